@@ -1,0 +1,771 @@
+// FlashAttention-2 backward with additive (T5) bias for sm_100a: dQ, dK, dV and the dS tiles that
+// become dBias, in ONE fused kernel (5 tensor-core contractions per tile instead of the
+// reference's 7), plus three small helper kernels (delta, dQ convert, dBias reduce).
+//
+// Replaces /root/reference/src/model/ops/flash_attention_v2_bias.py:
+//   _bwd_preprocess :516-556, _bwd_kv_kernel :559-745, _bwd_q_kernel :748-905, ds.sum(0) :214-215.
+//
+// One CTA = one (batch, head, 128-key block).  K and V stay resident in shared memory; the CTA
+// walks the query sequence in 128-row blocks:
+//     S  = Q K^T            (SS MMA -> TMEM)          dP = dO V^T          (SS MMA -> TMEM)
+//     P  = exp(S*s + bias - L),  dS = P * (dP - delta)      (two warpgroups, 64 columns each)
+//     P, dS -> shared memory as 16-bit, 128B-swizzled [m][n] tiles
+//     dV += P^T dO,  dK += dS^T Q   (A = MN-major smem)     dQ_blk = dS K  (A = K-major smem)
+//     dS tile  -> global with a TMA store (per-batch dS workspace or dBias directly)
+//     dQ_blk   -> fp32 accumulator in global with a TMA reduce-add (cp.reduce.async.bulk.tensor)
+//
+//   warp 4 : TMA producer (K, V once; Q / dO ring)     warp 6 : TMA producer for bias halves
+//   warp 5 : tcgen05.mma issuer                        warps 0-3 and 8-11 : compute warpgroups
+//
+// TMEM columns: S [0,128) | dP [128,256) | dV [256,256+D) | dK [256+D,256+2D) | dQ [256+2D, 256+3D)
+// (D = 128: dQ aliases the S columns).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200t5 {
+
+namespace {
+
+constexpr int kBM = 128;
+constexpr int kBN = 128;
+constexpr int kHalfBytes = 128 * 64 * 2;   // one [128][64] 16-bit swizzled half tile
+constexpr float kLog2e = 1.4426950408889634f;
+
+template <int kD>
+struct BwdCfg {
+    static constexpr int kRowBytes = (kD >= 64 ? 64 : kD) * 2;
+    static constexpr int kBoxes = kD >= 64 ? kD / 64 : 1;
+    static constexpr int kBoxBytes = kBM * kRowBytes;
+    static constexpr int kTileBytes = kBM * kD * 2;
+    static constexpr uint32_t kSwizzle = kRowBytes == 128 ? kSwz128 : (kRowBytes == 64 ? kSwz64 : kSwz32);
+    static constexpr int kQStages = kD <= 64 ? 2 : 1;
+    static constexpr bool kLookahead = kQStages == 2;      // issue S/dP of block i+1 before the dV/dK/dQ of block i
+    // dQ staging (fp32, [128][min(D,32)] boxes) aliases the P tile (and the dS tile when D = 128)
+    static constexpr int kDqBoxCols = kD >= 32 ? 32 : kD;
+    static constexpr int kDqBoxes = kD / kDqBoxCols;
+    static constexpr int kDqBoxBytes = kBM * kDqBoxCols * 4;
+    static constexpr bool kDqAliasesDs = kDqBoxes * kDqBoxBytes > 2 * kHalfBytes;
+    static constexpr int kK = 0;
+    static constexpr int kV = kK + kTileBytes;
+    static constexpr int kQ = kV + kTileBytes;
+    static constexpr int kDO = kQ + kQStages * kTileBytes;
+    static constexpr int kBias = kDO + kQStages * kTileBytes;
+    static constexpr int kP = kBias + 2 * kHalfBytes;
+    static constexpr int kDS = kP + 2 * kHalfBytes;
+    static constexpr int kBars = kDS + 2 * kHalfBytes;
+    static constexpr int kNumBars = 1 + 2 * kQStages + 4 + 6;
+    static constexpr int kTmemSlot = kBars + kNumBars * 8;
+    static constexpr int kTotal = kTmemSlot + 16;
+    static constexpr int kColS = 0;
+    static constexpr int kColDP = 128;
+    static constexpr int kColDV = 256;
+    static constexpr int kColDK = 256 + kD;
+    static constexpr bool kDqAliasS = (256 + 3 * kD) > 512;
+    static constexpr int kColDQ = kDqAliasS ? 0 : 256 + 2 * kD;
+    // columns of dQ each compute warpgroup drains (D = 16: warpgroup 0 takes all of them)
+    static constexpr int kDqColsPerWg = kD >= 32 ? kD / 2 : kD;
+};
+
+template <int kN>
+__device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t* r) {
+    if constexpr (kN == 32) tmem_ld32(taddr, *reinterpret_cast<uint32_t(*)[32]>(r));
+    else tmem_ld16(taddr, *reinterpret_cast<uint32_t(*)[16]>(r));
+}
+
+}  // namespace
+
+template <int kD, bool kBf16, int kBiasMode, bool kCausal>
+__global__ void __launch_bounds__(384, 1)
+attn_bwd_kernel(const __grid_constant__ AttnBwdKernelParams p) {
+    using C = BwdCfg<kD>;
+    extern __shared__ __align__(1024) uint8_t smem[];
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // ---- work decode: batch fastest (bias tiles shared in L2), late key blocks first when causal ----
+    const int nnb = p.num_n_blocks;
+    int bid = blockIdx.x;
+    const int b = bid % p.B;
+    bid /= p.B;
+    const int nb = kCausal ? (bid % nnb) : (nnb - 1 - bid % nnb);   // causal: early key blocks see the most rows
+    const int h = bid / nnb;
+    const int col0 = nb * kBN;
+    const int pseq = p.N - p.M;
+
+    int i_start = 0;
+    if (kCausal) {
+        const int first_row = col0 - pseq;                      // first query row that sees key col0
+        i_start = first_row <= 0 ? 0 : first_row / kBM;
+    }
+    const int n_iter = p.num_m_blocks > i_start ? p.num_m_blocks - i_start : 0;
+
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kBars);
+    uint64_t* kv_full = bars;
+    uint64_t* qdo_full = bars + 1;
+    uint64_t* qdo_empty = qdo_full + C::kQStages;
+    uint64_t* b_full = qdo_empty + C::kQStages;    // [2] one per 64-column half
+    uint64_t* b_empty = b_full + 2;
+    uint64_t* sdp_full = b_empty + 2;
+    uint64_t* sdp_empty = sdp_full + 1;
+    uint64_t* pds_full = sdp_empty + 1;
+    uint64_t* dq_full = pds_full + 1;
+    uint64_t* dq_empty = dq_full + 1;
+    uint64_t* acc_full = dq_empty + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::kTmemSlot);
+
+    if (threadIdx.x == 0) {
+        if ((smem_u32(smem) & 1023u) != 0) {
+            printf("b200t5: dynamic smem base not 1024-byte aligned\n");
+            __trap();
+        }
+        mbar_init(kv_full, 1);
+        for (int i = 0; i < C::kQStages; ++i) {
+            mbar_init(qdo_full + i, 1);
+            mbar_init(qdo_empty + i, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(b_full + i, 1);
+            mbar_init(b_empty + i, 4);
+        }
+        mbar_init(sdp_full, 1);
+        mbar_init(sdp_empty, 8);
+        mbar_init(pds_full, 1);
+        mbar_init(dq_full, 1);
+        mbar_init(dq_empty, 1);
+        mbar_init(acc_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 5) tmem_alloc<512>(tmem_slot);
+    if (warp == 4 && lane == 0) {
+        tma_prefetch_desc(&p.map_q);
+        tma_prefetch_desc(&p.map_k);
+        tma_prefetch_desc(&p.map_v);
+        tma_prefetch_desc(&p.map_do);
+        tma_prefetch_desc(&p.map_dq);
+        if (kBiasMode == 1) {
+            tma_prefetch_desc(&p.map_bias);
+            tma_prefetch_desc(&p.map_ds);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const bool is_compute = (warp < 4) || (warp >= 8);
+
+    if (!is_compute) {
+        // =============================== control warps (4..7) ===============================
+        setmaxnreg_dec<64>();
+        if (warp == 4 && lane == 0 && n_iter > 0) {
+            // ---- K, V once; then the Q / dO ring ----
+            mbar_arrive_expect_tx(kv_full, 2 * C::kTileBytes);
+#pragma unroll
+            for (int bx = 0; bx < C::kBoxes; ++bx) {
+                tma_load_4d(smem + C::kK + bx * C::kBoxBytes, &p.map_k, kv_full, bx * 64, col0, h, b);
+                tma_load_4d(smem + C::kV + bx * C::kBoxBytes, &p.map_v, kv_full, bx * 64, col0, h, b);
+            }
+            for (int k = 0; k < n_iter; ++k) {
+                const int s = k % C::kQStages;
+                const int mrow0 = (i_start + k) * kBM;
+                mbar_wait(qdo_empty + s, ((k / C::kQStages) & 1) ^ 1);
+                mbar_arrive_expect_tx(qdo_full + s, 2 * C::kTileBytes);
+#pragma unroll
+                for (int bx = 0; bx < C::kBoxes; ++bx) {
+                    tma_load_4d(smem + C::kQ + s * C::kTileBytes + bx * C::kBoxBytes, &p.map_q, qdo_full + s, bx * 64,
+                                mrow0, h, b);
+                    tma_load_4d(smem + C::kDO + s * C::kTileBytes + bx * C::kBoxBytes, &p.map_do, qdo_full + s,
+                                bx * 64, mrow0, h, b);
+                }
+            }
+        } else if (warp == 6 && lane == 0 && kBiasMode == 1) {
+            const int hb = p.bias_h_bcast ? 0 : h;
+            const int bb = p.bias_b_bcast ? 0 : b;
+            for (int k = 0; k < n_iter; ++k) {
+                const int mrow0 = (i_start + k) * kBM;
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    mbar_wait(b_empty + hh, (k & 1) ^ 1);
+                    mbar_arrive_expect_tx(b_full + hh, kHalfBytes);
+                    tma_load_4d(smem + C::kBias + hh * kHalfBytes, &p.map_bias, b_full + hh, col0 + hh * 64, mrow0, hb,
+                                bb);
+                }
+            }
+        } else if (warp == 5 && lane == 0 && n_iter > 0) {
+            // ---- MMA issuer ----
+            constexpr uint32_t idesc_s = make_idesc(kBf16, 128, 128, false, false);    // S, dP
+            constexpr uint32_t idesc_dkv = make_idesc(kBf16, 128, kD, true, true);     // dV, dK
+            constexpr uint32_t idesc_dq = make_idesc(kBf16, 128, kD, false, true);     // dQ
+            constexpr uint32_t sbo = 8 * C::kRowBytes;
+            const uint32_t k_addr = smem_u32(smem + C::kK);
+            const uint32_t v_addr = smem_u32(smem + C::kV);
+            const uint32_t p_addr = smem_u32(smem + C::kP);
+            const uint32_t ds_addr = smem_u32(smem + C::kDS);
+            const uint32_t tm_s = tmem_base + C::kColS;
+            const uint32_t tm_dp = tmem_base + C::kColDP;
+            const uint32_t tm_dv = tmem_base + C::kColDV;
+            const uint32_t tm_dk = tmem_base + C::kColDK;
+            const uint32_t tm_dq = tmem_base + C::kColDQ;
+
+            auto issue_s_dp = [&](int k) {
+                const int s = k % C::kQStages;
+                const uint32_t q_addr = smem_u32(smem + C::kQ + s * C::kTileBytes);
+                const uint32_t do_addr = smem_u32(smem + C::kDO + s * C::kTileBytes);
+#pragma unroll
+                for (int kk = 0; kk < kD / 16; ++kk) {
+                    const uint32_t off = (kk / 4) * C::kBoxBytes + (kk % 4) * 32;
+                    umma_ss(tm_s, make_sdesc(q_addr + off, 16, sbo, C::kSwizzle),
+                            make_sdesc(k_addr + off, 16, sbo, C::kSwizzle), idesc_s, kk > 0 ? 1u : 0u);
+                }
+#pragma unroll
+                for (int kk = 0; kk < kD / 16; ++kk) {
+                    const uint32_t off = (kk / 4) * C::kBoxBytes + (kk % 4) * 32;
+                    umma_ss(tm_dp, make_sdesc(do_addr + off, 16, sbo, C::kSwizzle),
+                            make_sdesc(v_addr + off, 16, sbo, C::kSwizzle), idesc_s, kk > 0 ? 1u : 0u);
+                }
+                umma_commit(sdp_full);
+            };
+            auto issue_grads = [&](int k) {
+                const int s = k % C::kQStages;
+                const uint32_t q_addr = smem_u32(smem + C::kQ + s * C::kTileBytes);
+                const uint32_t do_addr = smem_u32(smem + C::kDO + s * C::kTileBytes);
+                const uint32_t acc = k > 0 ? 1u : 0u;
+                // dV += P^T dO ; dK += dS^T Q      (K dimension = the 128 query rows of this block)
+#pragma unroll
+                for (int kk = 0; kk < kBM / 16; ++kk) {
+                    umma_ss(tm_dv, make_sdesc(p_addr + kk * 2048, kHalfBytes, 1024, kSwz128),
+                            make_sdesc(do_addr + kk * 16 * C::kRowBytes, C::kBoxBytes, sbo, C::kSwizzle), idesc_dkv,
+                            (acc | (kk > 0)) ? 1u : 0u);
+                }
+#pragma unroll
+                for (int kk = 0; kk < kBM / 16; ++kk) {
+                    umma_ss(tm_dk, make_sdesc(ds_addr + kk * 2048, kHalfBytes, 1024, kSwz128),
+                            make_sdesc(q_addr + kk * 16 * C::kRowBytes, C::kBoxBytes, sbo, C::kSwizzle), idesc_dkv,
+                            (acc | (kk > 0)) ? 1u : 0u);
+                }
+                umma_commit(qdo_empty + s);
+                // dQ_blk = dS K                    (K dimension = the 128 keys of this CTA)
+                if (k > 0) {
+                    mbar_wait(dq_empty, (k - 1) & 1);
+                    tc_fence_after();
+                }
+#pragma unroll
+                for (int kk = 0; kk < kBN / 16; ++kk) {
+                    umma_ss(tm_dq, make_sdesc(ds_addr + (kk / 4) * kHalfBytes + (kk % 4) * 32, 16, 1024, kSwz128),
+                            make_sdesc(k_addr + kk * 16 * C::kRowBytes, C::kBoxBytes, sbo, C::kSwizzle), idesc_dq,
+                            kk > 0 ? 1u : 0u);
+                }
+                umma_commit(dq_full);
+            };
+
+            mbar_wait(kv_full, 0);
+            if (C::kLookahead) {
+                mbar_wait(qdo_full + 0, 0);
+                tc_fence_after();
+                issue_s_dp(0);
+                for (int k = 0; k < n_iter; ++k) {
+                    if (k + 1 < n_iter) {
+                        const int kn = k + 1;
+                        mbar_wait(qdo_full + (kn % C::kQStages), (kn / C::kQStages) & 1);
+                        mbar_wait(sdp_empty, k & 1);
+                        tc_fence_after();
+                        issue_s_dp(kn);
+                    }
+                    mbar_wait(pds_full, k & 1);
+                    tc_fence_after();
+                    issue_grads(k);
+                }
+            } else {
+                for (int k = 0; k < n_iter; ++k) {
+                    mbar_wait(qdo_full + 0, k & 1);
+                    if (k > 0) {
+                        mbar_wait(sdp_empty, (k - 1) & 1);
+                        if (C::kDqAliasS) mbar_wait(dq_empty, (k - 1) & 1);
+                    }
+                    tc_fence_after();
+                    issue_s_dp(k);
+                    mbar_wait(pds_full, k & 1);
+                    tc_fence_after();
+                    issue_grads(k);
+                }
+            }
+            umma_commit(acc_full);
+        }
+    } else {
+        // =============================== compute warpgroups ===============================
+        setmaxnreg_inc<208>();
+        const int wg = warp >= 8 ? 1 : 0;                    // which 64-column half of the tile
+        const int r = (warp & 3) * 32 + lane;                // row in the block == TMEM lane
+        const int ctid = wg * 128 + r;                       // 0..255 among compute threads
+        const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
+        const uint32_t tm_s = tmem_base + lane_off + C::kColS + wg * 64;
+        const uint32_t tm_dp = tmem_base + lane_off + C::kColDP + wg * 64;
+        const uint32_t tm_dq = tmem_base + lane_off + C::kColDQ + wg * C::kDqColsPerWg;
+        uint8_t* sP = smem + C::kP + wg * kHalfBytes + r * 128;
+        uint8_t* sDS = smem + C::kDS + wg * kHalfBytes + r * 128;
+        const uint8_t* sB = smem + C::kBias + wg * kHalfBytes + r * 128;
+        const int hb = p.bias_h_bcast ? 0 : h;
+        const int bb = p.bias_b_bcast ? 0 : b;
+        const float scale_log2 = p.sm_scale * kLog2e;
+
+        for (int k = 0; k < n_iter; ++k) {
+            const int mrow0 = (i_start + k) * kBM;
+            const int grow = mrow0 + r;
+            const bool row_ok = grow < p.M;
+            float L_log2 = INFINITY, dlt = 0.f;              // out-of-range rows: P = 0
+            if (row_ok) {
+                const int64_t ri = ((int64_t)b * p.H + h) * p.M + grow;
+                const float Lv = __ldg(p.lse + ri);
+                dlt = __ldg(p.delta + ri);
+                L_log2 = (Lv == -INFINITY) ? INFINITY : Lv * kLog2e;   // rows with no visible key: P = 0
+            }
+            int lim = p.N - col0 - wg * 64;                  // first masked column, relative to my half
+            if (kCausal) {
+                const int cl = grow + pseq + 1 - col0 - wg * 64;
+                lim = cl < lim ? cl : lim;
+            }
+            const bool need_mask = (col0 + kBN > p.N) || (kCausal && (col0 + kBN - 1 > mrow0 + pseq));
+
+            mbar_wait(sdp_full, k & 1);
+            tc_fence_after();
+            if (kBiasMode == 1) mbar_wait(b_full + wg, k & 1);
+
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                uint32_t sr[32], dr[32];
+                tmem_ld32(tm_s + ch * 32, sr);
+                tmem_ld32(tm_dp + ch * 32, dr);
+                tmem_ld_wait();
+                if (ch == 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(sdp_empty);
+                }
+                uint32_t pp[16], dd[16];
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8) {
+                    float bv[8];
+                    if (kBiasMode == 1) {
+                        const uint4 u = *reinterpret_cast<const uint4*>(sB + (((ch * 4 + c8) ^ (r & 7)) << 4));
+                        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 f = unpack2<kBf16>(w[e]);
+                            bv[2 * e] = f.x;
+                            bv[2 * e + 1] = f.y;
+                        }
+                    } else if (kBiasMode == 2) {
+                        const uint16_t* bp = reinterpret_cast<const uint16_t*>(p.bias) + (int64_t)bb * p.bias_sb +
+                                             (int64_t)hb * p.bias_sh + (int64_t)grow * p.bias_sm;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int c = col0 + wg * 64 + ch * 32 + c8 * 8 + e;
+                            bv[e] = (row_ok && c < p.N) ? to_float16bit<kBf16>(__ldg(bp + (int64_t)c * p.bias_sn)) : 0.f;
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) bv[e] = 0.f;
+                    }
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2) {
+                        float pv[2], dv[2];
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const int ci = c8 * 8 + e + q;                      // column inside this 32-chunk
+                            const float xs = fmaf(__uint_as_float(sr[ci]), scale_log2, bv[e + q] * kLog2e);
+                            float pe = ex2_approx(xs - L_log2);
+                            if (need_mask && (ch * 32 + ci >= lim)) pe = 0.f;
+                            pv[q] = pe;
+                            dv[q] = pe * (__uint_as_float(dr[ci]) - dlt);
+                        }
+                        pp[c8 * 4 + e / 2] = pack2<kBf16>(pv[0], pv[1]);
+                        dd[c8 * 4 + e / 2] = pack2<kBf16>(dv[0], dv[1]);
+                    }
+                }
+                if (ch == 0 && k > 0) {
+                    // previous block's TMA reads of the P / dS / staging buffers must be finished
+                    named_bar_sync(2, 256);
+                }
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8) {
+                    const int off = ((ch * 4 + c8) ^ (r & 7)) << 4;
+                    *reinterpret_cast<uint4*>(sP + off) = make_uint4(pp[c8 * 4], pp[c8 * 4 + 1], pp[c8 * 4 + 2], pp[c8 * 4 + 3]);
+                    *reinterpret_cast<uint4*>(sDS + off) = make_uint4(dd[c8 * 4], dd[c8 * 4 + 1], dd[c8 * 4 + 2], dd[c8 * 4 + 3]);
+                }
+                if (kBiasMode == 2) {
+                    // unaligned / odd-stride bias: dS goes out with plain 16-bit stores
+                    uint16_t* dp = reinterpret_cast<uint16_t*>(p.ds) + (int64_t)b * p.ds_sb + (int64_t)h * p.ds_sh +
+                                   (int64_t)grow * p.ds_sm;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int c = col0 + wg * 64 + ch * 32 + 2 * i;
+                        if (row_ok && c < p.N) dp[(int64_t)c * p.ds_sn] = static_cast<uint16_t>(dd[i] & 0xFFFFu);
+                        if (row_ok && c + 1 < p.N) dp[(int64_t)(c + 1) * p.ds_sn] = static_cast<uint16_t>(dd[i] >> 16);
+                    }
+                }
+            }
+            if (kBiasMode == 1) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(b_empty + wg);
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(1, 256);
+            if (ctid == 0) {
+                mbar_arrive(pds_full);
+                if (kBiasMode == 1) {
+                    tma_store_4d(&p.map_ds, smem + C::kDS, col0, mrow0, h, b);
+                    tma_store_4d(&p.map_ds, smem + C::kDS + kHalfBytes, col0 + 64, mrow0, h, b);
+                    bulk_commit_group();
+                    if (C::kDqAliasesDs) bulk_wait_group_read<0>();
+                }
+            }
+
+            // ---- dQ block: TMEM -> swizzled fp32 staging (aliases P) -> TMA reduce-add ----
+            mbar_wait(dq_full, k & 1);           // dV, dK, dQ MMAs of this block are complete
+            tc_fence_after();
+            if (C::kDqAliasesDs) named_bar_sync(3, 256);      // dS store has drained the dS tile
+            if (wg == 0 || kD >= 32) {
+                constexpr int kCols = C::kDqColsPerWg;
+                constexpr int kChunk = kCols >= 32 ? 32 : kCols;
+#pragma unroll
+                for (int c0 = 0; c0 < kCols; c0 += kChunk) {
+                    uint32_t q[kChunk];
+                    tmem_ld_n<kChunk>(tm_dq + c0, q);
+                    tmem_ld_wait();
+                    const int gcol = wg * C::kDqColsPerWg + c0;            // first dQ column of this chunk
+                    uint8_t* box = smem + C::kP + (gcol / C::kDqBoxCols) * C::kDqBoxBytes + r * (C::kDqBoxCols * 4);
+#pragma unroll
+                    for (int i = 0; i < kChunk; i += 4) {
+                        const int c16 = ((gcol % C::kDqBoxCols) + i) / 4;  // 16-byte chunk inside the box row
+                        const int off = (C::kDqBoxCols == 32) ? ((c16 ^ (r & 7)) << 4) : (c16 << 4);
+                        *reinterpret_cast<uint4*>(box + off) = make_uint4(q[i], q[i + 1], q[i + 2], q[i + 3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async_smem();
+            named_bar_sync(1, 256);
+            if (ctid == 0) {
+                mbar_arrive(dq_empty);
+#pragma unroll
+                for (int bx = 0; bx < C::kDqBoxes; ++bx) {
+                    asm volatile(
+                        "cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group"
+                        " [%0, {%2, %3, %4, %5}], [%1];"
+                        :
+                        : "l"(reinterpret_cast<uint64_t>(&p.map_dq)),
+                          "r"(smem_u32(smem + C::kP + bx * C::kDqBoxBytes)), "r"(bx * C::kDqBoxCols), "r"(mrow0),
+                          "r"(h), "r"(b)
+                        : "memory");
+                }
+                bulk_commit_group();
+                bulk_wait_group_read<0>();
+            }
+            // (the matching named_bar_sync(2) sits in front of the next block's first smem write)
+        }
+
+        // ---- epilogue: dV (warpgroup 0) and dK * sm_scale (warpgroup 1) ----
+        {
+            const int gn = col0 + r;
+            const bool row_ok = gn < p.N;
+            uint8_t* out_row = wg == 0
+                ? reinterpret_cast<uint8_t*>(p.dv) + 2 * ((int64_t)b * p.dv_sb + (int64_t)h * p.dv_sh + (int64_t)gn * p.dv_sn)
+                : reinterpret_cast<uint8_t*>(p.dk) + 2 * ((int64_t)b * p.dk_sb + (int64_t)h * p.dk_sh + (int64_t)gn * p.dk_sn);
+            const float sc = wg == 0 ? 1.f : p.sm_scale;
+            if (n_iter > 0) {
+                mbar_wait(acc_full, 0);
+                tc_fence_after();
+                const uint32_t tm_acc = tmem_base + lane_off + (wg == 0 ? C::kColDV : C::kColDK);
+                constexpr int kChunk = kD >= 32 ? 32 : 16;
+#pragma unroll
+                for (int c0 = 0; c0 < kD; c0 += kChunk) {
+                    uint32_t a[kChunk];
+                    tmem_ld_n<kChunk>(tm_acc + c0, a);
+                    tmem_ld_wait();
+                    if (row_ok) {
+#pragma unroll
+                        for (int i = 0; i < kChunk; i += 8) {
+                            uint4 out;
+                            out.x = pack2<kBf16>(__uint_as_float(a[i + 0]) * sc, __uint_as_float(a[i + 1]) * sc);
+                            out.y = pack2<kBf16>(__uint_as_float(a[i + 2]) * sc, __uint_as_float(a[i + 3]) * sc);
+                            out.z = pack2<kBf16>(__uint_as_float(a[i + 4]) * sc, __uint_as_float(a[i + 5]) * sc);
+                            out.w = pack2<kBf16>(__uint_as_float(a[i + 6]) * sc, __uint_as_float(a[i + 7]) * sc);
+                            *reinterpret_cast<uint4*>(out_row + 2 * (c0 + i)) = out;
+                        }
+                    }
+                }
+                tc_fence_before();
+            } else if (row_ok) {
+#pragma unroll
+                for (int c = 0; c < kD; c += 8) *reinterpret_cast<uint4*>(out_row + 2 * c) = make_uint4(0, 0, 0, 0);
+            }
+        }
+        if (ctid == 0) bulk_wait_group<0>();     // all TMA stores / reductions of this CTA have landed
+    }
+
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// helper kernels
+// ------------------------------------------------------------------------------------------
+// delta = rowsum(O * dO) in fp32 (reference: _bwd_preprocess :516-556) + zero the fp32 dQ accumulator.
+template <int kD, bool kBf16>
+__global__ void attn_bwd_preprocess_kernel(const uint8_t* __restrict__ o, int64_t o_sb, int64_t o_sh, int64_t o_sm,
+                                           const uint8_t* __restrict__ dout, int64_t do_sb, int64_t do_sh,
+                                           int64_t do_sm, float* __restrict__ delta, float* __restrict__ dq_acc, int B,
+                                           int H, int M) {
+    constexpr int kTpr = kD / 8;                              // threads per row, 8 elements (16 B) each
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t row = gid / kTpr;
+    const int part = static_cast<int>(gid % kTpr);
+    const int64_t rows = (int64_t)B * H * M;
+    float acc = 0.f;
+    if (row < rows) {
+        const int m = static_cast<int>(row % M);
+        const int64_t bh = row / M;
+        const int hh = static_cast<int>(bh % H);
+        const int64_t bb = bh / H;
+        const uint4 ov = *reinterpret_cast<const uint4*>(o + 2 * (bb * o_sb + hh * o_sh + m * o_sm + part * 8));
+        const uint4 dv = *reinterpret_cast<const uint4*>(dout + 2 * (bb * do_sb + hh * do_sh + m * do_sm + part * 8));
+        const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w};
+        const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 a = unpack2<kBf16>(ow[e]);
+            const float2 c = unpack2<kBf16>(dw[e]);
+            acc = fmaf(a.x, c.x, acc);
+            acc = fmaf(a.y, c.y, acc);
+        }
+        float4* z = reinterpret_cast<float4*>(dq_acc + row * kD + part * 8);
+        z[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        z[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int off = kTpr / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (row < rows && part == 0) delta[row] = acc;
+}
+
+template <int kD, bool kBf16>
+__global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ dq_acc, uint8_t* __restrict__ dq, int64_t sb,
+                                           int64_t sh, int64_t sm, int B, int H, int M, float scale) {
+    constexpr int kTpr = kD / 8;
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t row = gid / kTpr;
+    const int part = static_cast<int>(gid % kTpr);
+    if (row >= (int64_t)B * H * M) return;
+    const int m = static_cast<int>(row % M);
+    const int64_t bh = row / M;
+    const int hh = static_cast<int>(bh % H);
+    const int64_t bb = bh / H;
+    const float4 a = *reinterpret_cast<const float4*>(dq_acc + row * kD + part * 8);
+    const float4 c = *reinterpret_cast<const float4*>(dq_acc + row * kD + part * 8 + 4);
+    uint4 out;
+    out.x = pack2<kBf16>(a.x * scale, a.y * scale);
+    out.y = pack2<kBf16>(a.z * scale, a.w * scale);
+    out.z = pack2<kBf16>(c.x * scale, c.y * scale);
+    out.w = pack2<kBf16>(c.z * scale, c.w * scale);
+    *reinterpret_cast<uint4*>(dq + 2 * (bb * sb + hh * sh + m * sm + part * 8)) = out;
+}
+
+// dBias = sum of the per-(batch, head) dS tiles over every broadcast dimension, fp32 accumulation,
+// one rounding (reference: ds.sum(0) :214-215; the head sum is the fix described in SURVEY.md section 4).
+template <bool kBf16>
+__global__ void dbias_reduce_kernel(const uint16_t* __restrict__ ws, uint16_t* __restrict__ out, int64_t o_sb,
+                                    int64_t o_sh, int64_t o_sm, int64_t o_sn, int B, int H, int M, int N, int reduce_b,
+                                    int reduce_h, int causal) {
+    const int64_t mn = (int64_t)M * N;
+    const int ob_n = reduce_b ? 1 : B;
+    const int oh_n = reduce_h ? 1 : H;
+    const int64_t total = (int64_t)ob_n * oh_n * mn;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int n = static_cast<int>(idx % N);
+        int64_t t = idx / N;
+        const int m = static_cast<int>(t % M);
+        t /= M;
+        const int oh = static_cast<int>(t % oh_n);
+        const int ob = static_cast<int>(t / oh_n);
+        float acc = 0.f;
+        if (!(causal && n > m + (N - M))) {
+            const int b0 = reduce_b ? 0 : ob, b1 = reduce_b ? B : ob + 1;
+            const int h0 = reduce_h ? 0 : oh, h1 = reduce_h ? H : oh + 1;
+            for (int bb = b0; bb < b1; ++bb)
+                for (int hh = h0; hh < h1; ++hh)
+                    acc += to_float16bit<kBf16>(ws[((int64_t)bb * H + hh) * mn + (int64_t)m * N + n]);
+        }
+        const uint32_t packed = pack2<kBf16>(acc, 0.f);
+        out[ob * o_sb + oh * o_sh + m * o_sm + n * o_sn] = static_cast<uint16_t>(packed & 0xFFFFu);
+    }
+}
+
+// 8 columns per thread (16-byte loads), N % 8 == 0 and contiguous output rows
+template <bool kBf16>
+__global__ void dbias_reduce_vec8_kernel(const uint4* __restrict__ ws, uint4* __restrict__ out, int B, int H, int M,
+                                         int N, int reduce_b, int reduce_h, int causal) {
+    const int n8 = N / 8;
+    const int64_t mn8 = (int64_t)M * n8;
+    const int ob_n = reduce_b ? 1 : B;
+    const int oh_n = reduce_h ? 1 : H;
+    const int64_t total = (int64_t)ob_n * oh_n * mn8;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int c8 = static_cast<int>(idx % n8);
+        int64_t t = idx / n8;
+        const int m = static_cast<int>(t % M);
+        t /= M;
+        const int oh = static_cast<int>(t % oh_n);
+        const int ob = static_cast<int>(t / oh_n);
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+        const int vis = causal ? (m + (N - M) + 1 - c8 * 8) : 8;      // visible columns of this group
+        if (vis > 0) {
+            const int b0 = reduce_b ? 0 : ob, b1 = reduce_b ? B : ob + 1;
+            const int h0 = reduce_h ? 0 : oh, h1 = reduce_h ? H : oh + 1;
+            for (int bb = b0; bb < b1; ++bb)
+                for (int hh = h0; hh < h1; ++hh) {
+                    const uint4 u = __ldg(ws + ((int64_t)bb * H + hh) * mn8 + (int64_t)m * n8 + c8);
+                    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 f = unpack2<kBf16>(w[e]);
+                        acc[2 * e] += f.x;
+                        acc[2 * e + 1] += f.y;
+                    }
+                }
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                if (e >= vis) acc[e] = 0.f;
+        }
+        uint4 o;
+        o.x = pack2<kBf16>(acc[0], acc[1]);
+        o.y = pack2<kBf16>(acc[2], acc[3]);
+        o.z = pack2<kBf16>(acc[4], acc[5]);
+        o.w = pack2<kBf16>(acc[6], acc[7]);
+        out[idx] = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side launchers
+// ------------------------------------------------------------------------------------------
+template <int kD, bool kBf16, int kBiasMode, bool kCausal>
+static cudaError_t launch_bwd_inst(const AttnBwdKernelParams& kp, cudaStream_t stream) {
+    using C = BwdCfg<kD>;
+    auto kern = attn_bwd_kernel<kD, kBf16, kBiasMode, kCausal>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal);
+    if (e != cudaSuccess) return e;
+    const int grid = kp.B * kp.H * kp.num_n_blocks;
+    kern<<<grid, 384, C::kTotal, stream>>>(kp);
+    return cudaGetLastError();
+}
+
+template <int kD, bool kBf16>
+static cudaError_t launch_bwd_d(const AttnBwdKernelParams& kp, int bias_mode, bool causal, cudaStream_t stream) {
+    switch (bias_mode * 2 + (causal ? 1 : 0)) {
+        case 0: return launch_bwd_inst<kD, kBf16, 0, false>(kp, stream);
+        case 1: return launch_bwd_inst<kD, kBf16, 0, true>(kp, stream);
+        case 2: return launch_bwd_inst<kD, kBf16, 1, false>(kp, stream);
+        case 3: return launch_bwd_inst<kD, kBf16, 1, true>(kp, stream);
+        case 4: return launch_bwd_inst<kD, kBf16, 2, false>(kp, stream);
+        default: return launch_bwd_inst<kD, kBf16, 2, true>(kp, stream);
+    }
+}
+
+cudaError_t launch_attn_bwd(const AttnBwdKernelParams& kp, int D, bool bf16, int bias_mode, bool causal,
+                            cudaStream_t stream) {
+#define B200T5_BWD_CASE(DD)                                                              \
+    case DD:                                                                             \
+        return bf16 ? launch_bwd_d<DD, true>(kp, bias_mode, causal, stream)              \
+                    : launch_bwd_d<DD, false>(kp, bias_mode, causal, stream);
+    switch (D) {
+        B200T5_BWD_CASE(16)
+        B200T5_BWD_CASE(32)
+        B200T5_BWD_CASE(64)
+        B200T5_BWD_CASE(128)
+        default: return cudaErrorInvalidValue;
+    }
+#undef B200T5_BWD_CASE
+}
+
+cudaError_t launch_attn_bwd_preprocess(const void* o, const int64_t* os, const void* dout, const int64_t* ds,
+                                       float* delta, float* dq_acc, int B, int H, int M, int D, bool bf16,
+                                       cudaStream_t stream) {
+    const int64_t threads = (int64_t)B * H * M * (D / 8);
+    const int block = 256;
+    const int grid = static_cast<int>((threads + block - 1) / block);
+#define B200T5_PRE(DD, BF)                                                                                         \
+    attn_bwd_preprocess_kernel<DD, BF><<<grid, block, 0, stream>>>(                                                \
+        static_cast<const uint8_t*>(o), os[0], os[1], os[2], static_cast<const uint8_t*>(dout), ds[0], ds[1],     \
+        ds[2], delta, dq_acc, B, H, M)
+    switch (D) {
+        case 16: if (bf16) B200T5_PRE(16, true); else B200T5_PRE(16, false); break;
+        case 32: if (bf16) B200T5_PRE(32, true); else B200T5_PRE(32, false); break;
+        case 64: if (bf16) B200T5_PRE(64, true); else B200T5_PRE(64, false); break;
+        case 128: if (bf16) B200T5_PRE(128, true); else B200T5_PRE(128, false); break;
+        default: return cudaErrorInvalidValue;
+    }
+#undef B200T5_PRE
+    return cudaGetLastError();
+}
+
+cudaError_t launch_attn_bwd_dq_convert(const float* dq_acc, void* dq, const int64_t* s, int B, int H, int M, int D,
+                                       float sm_scale, bool bf16, cudaStream_t stream) {
+    const int64_t threads = (int64_t)B * H * M * (D / 8);
+    const int block = 256;
+    const int grid = static_cast<int>((threads + block - 1) / block);
+#define B200T5_CVT(DD, BF)                                                                                  \
+    attn_bwd_dq_convert_kernel<DD, BF><<<grid, block, 0, stream>>>(dq_acc, static_cast<uint8_t*>(dq), s[0], \
+                                                                    s[1], s[2], B, H, M, sm_scale)
+    switch (D) {
+        case 16: if (bf16) B200T5_CVT(16, true); else B200T5_CVT(16, false); break;
+        case 32: if (bf16) B200T5_CVT(32, true); else B200T5_CVT(32, false); break;
+        case 64: if (bf16) B200T5_CVT(64, true); else B200T5_CVT(64, false); break;
+        case 128: if (bf16) B200T5_CVT(128, true); else B200T5_CVT(128, false); break;
+        default: return cudaErrorInvalidValue;
+    }
+#undef B200T5_CVT
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dbias_reduce(const void* ds_ws, void* dbias, const int64_t* s, int B, int H, int M, int N,
+                                int reduce_b, int reduce_h, bool causal, bool bf16, cudaStream_t stream) {
+    const int ob = reduce_b ? 1 : B, oh = reduce_h ? 1 : H;
+    const bool contiguous = s[3] == 1 && s[2] == N && (oh == 1 || s[1] == (int64_t)M * N) &&
+                            (ob == 1 || s[0] == (int64_t)oh * M * N);
+    const bool vec = contiguous && (N % 8 == 0) && ((reinterpret_cast<uintptr_t>(dbias) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(ds_ws) & 15) == 0);
+    const int block = 256;
+    if (vec) {
+        const int64_t total = (int64_t)ob * oh * M * (N / 8);
+        const int grid = static_cast<int>(std::min<int64_t>((total + block - 1) / block, 148 * 16));
+        if (bf16)
+            dbias_reduce_vec8_kernel<true><<<grid, block, 0, stream>>>(static_cast<const uint4*>(ds_ws),
+                                                                       static_cast<uint4*>(dbias), B, H, M, N,
+                                                                       reduce_b, reduce_h, causal ? 1 : 0);
+        else
+            dbias_reduce_vec8_kernel<false><<<grid, block, 0, stream>>>(static_cast<const uint4*>(ds_ws),
+                                                                        static_cast<uint4*>(dbias), B, H, M, N,
+                                                                        reduce_b, reduce_h, causal ? 1 : 0);
+    } else {
+        const int64_t total = (int64_t)ob * oh * M * N;
+        const int grid = static_cast<int>(std::min<int64_t>((total + block - 1) / block, 148 * 16));
+        if (bf16)
+            dbias_reduce_kernel<true><<<grid, block, 0, stream>>>(static_cast<const uint16_t*>(ds_ws),
+                                                                  static_cast<uint16_t*>(dbias), s[0], s[1], s[2],
+                                                                  s[3], B, H, M, N, reduce_b, reduce_h, causal ? 1 : 0);
+        else
+            dbias_reduce_kernel<false><<<grid, block, 0, stream>>>(static_cast<const uint16_t*>(ds_ws),
+                                                                   static_cast<uint16_t*>(dbias), s[0], s[1], s[2],
+                                                                   s[3], B, H, M, N, reduce_b, reduce_h, causal ? 1 : 0);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace b200t5

@@ -1,0 +1,471 @@
+// FlashAttention-2 forward with additive (T5) bias for sm_100a.
+//
+// Replaces /root/reference/src/model/ops/flash_attention_v2_bias.py:327-483 (`_fwd_kernel`).
+//
+// One CTA = one (batch, head, 128-row query block); it walks the key/value sequence in 128-wide
+// tiles.  Two CTAs are resident per SM (D <= 64) so one CTA's softmax overlaps the other's MMAs.
+//
+//   warp 4 (1 lane)  : TMA producer for Q (once) and the K / V ring (2 stages each)
+//   warp 6 (1 lane)  : TMA producer for the bias ring (2 stages of 128 rows x 64 columns)
+//   warp 5 (1 lane)  : tcgen05.mma issuer   S = Q K^T (SS)  and  O += P V (A = P from TMEM)
+//   warps 0-3        : one thread per query row: tcgen05.ld S, bias add, online softmax (lazy
+//                      rescale of O in TMEM), P -> TMEM as packed 16-bit, epilogue O / l and LSE
+//
+// TMEM columns: S [0,128) fp32 | O [128,128+D) fp32 | P [128+D, 128+D+64) packed 16-bit pairs.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200t5 {
+
+namespace {
+
+constexpr int kBM = 128;   // query rows per CTA
+constexpr int kBN = 128;   // keys per tile
+constexpr int kKVStages = 2;
+constexpr int kBiasStages = 2;
+constexpr int kBiasHalfBytes = kBM * 64 * 2;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr float kRescaleThreshold = 8.0f * kLn2;   // keep a stale max while exp(x - m) <= 256
+
+template <int kD>
+struct FwdSmem {
+    static constexpr int kRowBytes = (kD >= 64 ? 64 : kD) * 2;   // bytes per smem row inside one swizzle box
+    static constexpr int kBoxes = kD >= 64 ? kD / 64 : 1;        // 64-column TMA boxes per operand row
+    static constexpr int kTileBytes = kBM * kD * 2;              // Q, K or V tile
+    static constexpr int kBoxBytes = kBM * kRowBytes;
+    static constexpr int kQ = 0;
+    static constexpr int kK = kQ + kTileBytes;
+    static constexpr int kV = kK + kKVStages * kTileBytes;
+    static constexpr int kBias = kV + kKVStages * kTileBytes;
+    static constexpr int kBars = kBias + kBiasStages * kBiasHalfBytes;
+    static constexpr int kNumBars = 1 + 4 * kKVStages + 2 * kBiasStages + 4;
+    static constexpr int kTmemSlot = kBars + kNumBars * 8;
+    static constexpr int kTotal = kTmemSlot + 16;
+    static constexpr uint32_t kSwizzle = kRowBytes == 128 ? kSwz128 : (kRowBytes == 64 ? kSwz64 : kSwz32);
+    static constexpr int kTmemCols = (128 + kD + 64) <= 256 ? 256 : 512;
+    static constexpr int kOCol = 128;
+    static constexpr int kPCol = 128 + kD;
+};
+
+struct FwdBars {
+    uint64_t* q_full;
+    uint64_t* k_full;    // [kKVStages]
+    uint64_t* k_empty;
+    uint64_t* v_full;
+    uint64_t* v_empty;
+    uint64_t* b_full;    // [kBiasStages]
+    uint64_t* b_empty;
+    uint64_t* s_full;
+    uint64_t* s_empty;
+    uint64_t* p_full;
+    uint64_t* pv_done;
+};
+
+}  // namespace
+
+template <int kD, bool kBf16, int kBiasMode, bool kCausal>
+__global__ void __launch_bounds__(256, 2)   // 128 regs at launch; setmaxnreg re-splits them per role
+attn_fwd_kernel(const __grid_constant__ AttnFwdKernelParams p) {
+    using L = FwdSmem<kD>;
+    extern __shared__ __align__(1024) uint8_t smem[];
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // ---- work decode: batch fastest so the CTAs sharing a bias tile run together (L2 reuse) ----
+    const int nmb = p.num_m_blocks;
+    int bid = blockIdx.x;
+    const int b = bid % p.B;
+    bid /= p.B;
+    const int mb = nmb - 1 - (bid % nmb);     // heavy (late) causal blocks first
+    const int h = bid / nmb;
+    const int row0 = mb * kBM;
+    const int pseq = p.N - p.M;
+
+    int num_tiles = (p.N + kBN - 1) / kBN;
+    if (kCausal) {
+        const int last_col = row0 + kBM - 1 + pseq;          // last visible key of the last row
+        const int t = last_col < 0 ? 0 : last_col / kBN + 1;
+        num_tiles = t < num_tiles ? t : num_tiles;
+    }
+
+    FwdBars bars;
+    {
+        uint64_t* bb = reinterpret_cast<uint64_t*>(smem + L::kBars);
+        bars.q_full = bb;
+        bars.k_full = bb + 1;
+        bars.k_empty = bars.k_full + kKVStages;
+        bars.v_full = bars.k_empty + kKVStages;
+        bars.v_empty = bars.v_full + kKVStages;
+        bars.b_full = bars.v_empty + kKVStages;
+        bars.b_empty = bars.b_full + kBiasStages;
+        bars.s_full = bars.b_empty + kBiasStages;
+        bars.s_empty = bars.s_full + 1;
+        bars.p_full = bars.s_empty + 1;
+        bars.pv_done = bars.p_full + 1;
+    }
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kTmemSlot);
+
+    if (threadIdx.x == 0) {
+        if ((smem_u32(smem) & 1023u) != 0) {
+            printf("b200t5: dynamic smem base not 1024-byte aligned\n");
+            __trap();
+        }
+        mbar_init(bars.q_full, 1);
+        for (int i = 0; i < kKVStages; ++i) {
+            mbar_init(bars.k_full + i, 1);
+            mbar_init(bars.k_empty + i, 1);
+            mbar_init(bars.v_full + i, 1);
+            mbar_init(bars.v_empty + i, 1);
+        }
+        for (int i = 0; i < kBiasStages; ++i) {
+            mbar_init(bars.b_full + i, 1);
+            mbar_init(bars.b_empty + i, 4);
+        }
+        mbar_init(bars.s_full, 1);
+        mbar_init(bars.s_empty, 4);
+        mbar_init(bars.p_full, 4);
+        mbar_init(bars.pv_done, 1);
+        fence_mbar_init();
+    }
+    if (warp == 5) tmem_alloc<L::kTmemCols>(tmem_slot);
+    if (warp == 4 && lane == 0) {
+        tma_prefetch_desc(&p.map_q);
+        tma_prefetch_desc(&p.map_k);
+        tma_prefetch_desc(&p.map_v);
+        if (kBiasMode == 1) tma_prefetch_desc(&p.map_bias);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp >= 4) {
+        // =============================== control warps ===============================
+        setmaxnreg_dec<48>();
+        if (warp == 4 && lane == 0 && num_tiles > 0) {
+            // ---- Q / K / V producer ----
+            mbar_arrive_expect_tx(bars.q_full, L::kTileBytes);
+#pragma unroll
+            for (int bx = 0; bx < L::kBoxes; ++bx)
+                tma_load_4d(smem + L::kQ + bx * L::kBoxBytes, &p.map_q, bars.q_full, bx * 64, row0, h, b);
+            for (int j = 0; j < num_tiles; ++j) {
+                const int s = j % kKVStages;
+                const uint32_t par = ((j / kKVStages) & 1) ^ 1;
+                mbar_wait(bars.k_empty + s, par);
+                mbar_arrive_expect_tx(bars.k_full + s, L::kTileBytes);
+#pragma unroll
+                for (int bx = 0; bx < L::kBoxes; ++bx)
+                    tma_load_4d(smem + L::kK + s * L::kTileBytes + bx * L::kBoxBytes, &p.map_k, bars.k_full + s,
+                                bx * 64, j * kBN, h, b);
+                mbar_wait(bars.v_empty + s, par);
+                mbar_arrive_expect_tx(bars.v_full + s, L::kTileBytes);
+#pragma unroll
+                for (int bx = 0; bx < L::kBoxes; ++bx)
+                    tma_load_4d(smem + L::kV + s * L::kTileBytes + bx * L::kBoxBytes, &p.map_v, bars.v_full + s,
+                                bx * 64, j * kBN, h, b);
+            }
+        } else if (warp == 6 && lane == 0 && kBiasMode == 1) {
+            // ---- bias producer: two 64-column halves per tile ----
+            const int hb = p.bias_h_bcast ? 0 : h;
+            const int bb = p.bias_b_bcast ? 0 : b;
+            for (int it = 0; it < 2 * num_tiles; ++it) {
+                const int s = it % kBiasStages;
+                const uint32_t par = ((it / kBiasStages) & 1) ^ 1;
+                mbar_wait(bars.b_empty + s, par);
+                mbar_arrive_expect_tx(bars.b_full + s, kBiasHalfBytes);
+                tma_load_4d(smem + L::kBias + s * kBiasHalfBytes, &p.map_bias, bars.b_full + s,
+                            (it >> 1) * kBN + (it & 1) * 64, row0, hb, bb);
+            }
+        } else if (warp == 5 && lane == 0 && num_tiles > 0) {
+            // ---- MMA issuer ----
+            constexpr uint32_t idesc_s = make_idesc(kBf16, kBM, kBN, false, false);
+            constexpr uint32_t idesc_pv = make_idesc(kBf16, kBM, kD, false, true);
+            constexpr uint32_t sbo = 8 * L::kRowBytes;
+            const uint32_t q_addr = smem_u32(smem + L::kQ);
+            const uint32_t tm_s = tmem_base;
+            const uint32_t tm_o = tmem_base + L::kOCol;
+            const uint32_t tm_p = tmem_base + L::kPCol;
+
+            auto issue_s = [&](int j) {
+                const int s = j % kKVStages;
+                const uint32_t k_addr = smem_u32(smem + L::kK + s * L::kTileBytes);
+#pragma unroll
+                for (int kk = 0; kk < kD / 16; ++kk) {
+                    // K-major operands: 16 elements of K per MMA = 32 bytes inside a swizzled row
+                    const uint32_t off = (kk / 4) * L::kBoxBytes + (kk % 4) * 32;
+                    umma_ss(tm_s, make_sdesc(q_addr + off, 16, sbo, L::kSwizzle),
+                            make_sdesc(k_addr + off, 16, sbo, L::kSwizzle), idesc_s, kk > 0 ? 1u : 0u);
+                }
+                umma_commit(bars.s_full);
+                umma_commit(bars.k_empty + s);
+            };
+
+            mbar_wait(bars.q_full, 0);
+            mbar_wait(bars.k_full + 0, 0);
+            tc_fence_after();
+            issue_s(0);
+            for (int j = 0; j < num_tiles; ++j) {
+                if (j + 1 < num_tiles) {
+                    const int jn = j + 1;
+                    mbar_wait(bars.k_full + (jn % kKVStages), (jn / kKVStages) & 1);
+                    mbar_wait(bars.s_empty, j & 1);
+                    tc_fence_after();
+                    issue_s(jn);
+                }
+                const int s = j % kKVStages;
+                mbar_wait(bars.v_full + s, (j / kKVStages) & 1);
+                mbar_wait(bars.p_full, j & 1);
+                tc_fence_after();
+                const uint32_t v_addr = smem_u32(smem + L::kV + s * L::kTileBytes);
+#pragma unroll
+                for (int kk = 0; kk < kBN / 16; ++kk) {
+                    // B = V, MN-major: 16 key rows per MMA; LBO = stride between 64-wide d chunks
+                    umma_ts(tm_o, tm_p + kk * 8,
+                            make_sdesc(v_addr + kk * 16 * L::kRowBytes, L::kBoxBytes, sbo, L::kSwizzle), idesc_pv,
+                            (j > 0 || kk > 0) ? 1u : 0u);
+                }
+                umma_commit(bars.pv_done);
+                umma_commit(bars.v_empty + s);
+            }
+        }
+    } else {
+        // =============================== softmax warpgroup ===============================
+        setmaxnreg_inc<208>();
+        const int r = threadIdx.x;                 // row inside the tile == TMEM lane
+        const int grow = row0 + r;                 // global query row
+        const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+        const uint32_t tm_s = tmem_base + lane_off;
+        const uint32_t tm_o = tmem_base + lane_off + L::kOCol;
+        const uint32_t tm_p = tmem_base + lane_off + L::kPCol;
+
+        float m_ref = -INFINITY;   // running reference max (natural units, scaled + biased scores)
+        float l_sum = 0.f;
+
+        const uint16_t* bias_row = nullptr;
+        if (kBiasMode == 2) {
+            bias_row = reinterpret_cast<const uint16_t*>(p.bias) + (p.bias_b_bcast ? 0 : (int64_t)b * p.bias_sb) +
+                       (p.bias_h_bcast ? 0 : (int64_t)h * p.bias_sh) + (int64_t)grow * p.bias_sm;
+        }
+
+        for (int j = 0; j < num_tiles; ++j) {
+            const int col0 = j * kBN;
+            float x[kBN];
+
+            mbar_wait(bars.s_full, j & 1);
+            tc_fence_after();
+            {
+                uint32_t(&xr)[kBN] = reinterpret_cast<uint32_t(&)[kBN]>(x);
+                tmem_ld32(tm_s + 0, reinterpret_cast<uint32_t(&)[32]>(xr[0]));
+                tmem_ld32(tm_s + 32, reinterpret_cast<uint32_t(&)[32]>(xr[32]));
+                tmem_ld32(tm_s + 64, reinterpret_cast<uint32_t(&)[32]>(xr[64]));
+                tmem_ld32(tm_s + 96, reinterpret_cast<uint32_t(&)[32]>(xr[96]));
+                tmem_ld_wait();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars.s_empty);
+
+            // ---- scores = S * sm_scale + bias ----
+            if (kBiasMode == 1) {
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int it = 2 * j + hh;
+                    const int s = it % kBiasStages;
+                    mbar_wait(bars.b_full + s, (it / kBiasStages) & 1);
+                    const uint8_t* brow = smem + L::kBias + s * kBiasHalfBytes + r * 128;
+#pragma unroll
+                    for (int c8 = 0; c8 < 8; ++c8) {
+                        const uint4 u = *reinterpret_cast<const uint4*>(brow + ((c8 ^ (r & 7)) << 4));
+                        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 f = unpack2<kBf16>(w[e]);
+                            const int c = hh * 64 + c8 * 8 + e * 2;
+                            x[c] = fmaf(x[c], p.sm_scale, f.x);
+                            x[c + 1] = fmaf(x[c + 1], p.sm_scale, f.y);
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bars.b_empty + s);
+                }
+            } else if (kBiasMode == 2) {
+#pragma unroll
+                for (int c = 0; c < kBN; ++c) {
+                    float bv = 0.f;
+                    if (grow < p.M && col0 + c < p.N)
+                        bv = to_float16bit<kBf16>(__ldg(bias_row + (int64_t)(col0 + c) * p.bias_sn));
+                    x[c] = fmaf(x[c], p.sm_scale, bv);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < kBN; ++c) x[c] *= p.sm_scale;
+            }
+
+            // ---- masks: key tail and (bottom-right aligned) causal ----
+            {
+                int lim = p.N - col0;
+                if (kCausal) {
+                    const int cl = grow + pseq + 1 - col0;
+                    lim = cl < lim ? cl : lim;
+                }
+                const bool need_mask = (col0 + kBN > p.N) || (kCausal && (col0 + kBN - 1 > row0 + pseq));
+                if (need_mask) {
+#pragma unroll
+                    for (int c = 0; c < kBN; ++c)
+                        if (c >= lim) x[c] = -INFINITY;
+                }
+            }
+
+            // ---- online softmax with lazy rescale ----
+            float t0 = x[0], t1 = x[1], t2 = x[2], t3 = x[3];
+#pragma unroll
+            for (int c = 4; c < kBN; c += 4) {
+                t0 = fmaxf(t0, x[c]);
+                t1 = fmaxf(t1, x[c + 1]);
+                t2 = fmaxf(t2, x[c + 2]);
+                t3 = fmaxf(t3, x[c + 3]);
+            }
+            const float tmax = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3));
+            float alpha = 1.f;
+            if (tmax > m_ref + kRescaleThreshold) {       // also true for the first finite tile (m_ref = -inf)
+                alpha = __expf(m_ref - tmax);              // exp(-inf) = 0 on the first tile
+                m_ref = tmax;
+            }
+            const float m_safe = (m_ref == -INFINITY) ? 0.f : m_ref;
+            const float neg_m_log2 = -m_safe * kLog2e;
+
+            uint32_t pk[kBN / 2];
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int c = 0; c < kBN; c += 2) {
+                const float e0 = ex2_approx(fmaf(x[c], kLog2e, neg_m_log2));
+                const float e1 = ex2_approx(fmaf(x[c + 1], kLog2e, neg_m_log2));
+                s0 += e0;
+                s1 += e1;
+                pk[c / 2] = pack2<kBf16>(e0, e1);
+            }
+            l_sum = l_sum * alpha + (s0 + s1);
+
+            if (j > 0) {
+                mbar_wait(bars.pv_done, (j - 1) & 1);     // O and the P buffer are free again
+                tc_fence_after();
+                if (__any_sync(0xffffffffu, alpha != 1.f)) {
+#pragma unroll
+                    for (int c0 = 0; c0 < kD; c0 += 32) {
+                        if constexpr (kD >= 32) {
+                            uint32_t o[32];
+                            tmem_ld32(tm_o + c0, o);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                            tmem_st32(tm_o + c0, o);
+                        } else {
+                            uint32_t o[16];
+                            tmem_ld16(tm_o + c0, o);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                            tmem_st16(tm_o + c0, o);
+                        }
+                    }
+                }
+            }
+            tmem_st32(tm_p + 0, reinterpret_cast<const uint32_t(&)[32]>(pk[0]));
+            tmem_st32(tm_p + 32, reinterpret_cast<const uint32_t(&)[32]>(pk[32]));
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars.p_full);
+        }
+
+        // ---- epilogue: O / l -> global (row-contiguous 16-byte stores), LSE ----
+        const bool row_ok = grow < p.M;
+        uint8_t* o_row = reinterpret_cast<uint8_t*>(p.o) +
+                         2 * ((int64_t)b * p.o_sb + (int64_t)h * p.o_sh + (int64_t)grow * p.o_sm);
+        if (num_tiles > 0) {
+            mbar_wait(bars.pv_done, (num_tiles - 1) & 1);
+            tc_fence_after();
+            const float inv_l = l_sum > 0.f ? 1.f / l_sum : 0.f;
+            constexpr int kChunk = kD >= 32 ? 32 : 16;
+#pragma unroll
+            for (int c0 = 0; c0 < kD; c0 += kChunk) {
+                uint32_t o[kChunk];
+                if constexpr (kChunk == 32) tmem_ld32(tm_o + c0, o);
+                else tmem_ld16(tm_o + c0, reinterpret_cast<uint32_t(&)[16]>(o[0]));
+                tmem_ld_wait();
+                if (row_ok) {
+#pragma unroll
+                    for (int i = 0; i < kChunk; i += 8) {
+                        uint4 out;
+                        out.x = pack2<kBf16>(__uint_as_float(o[i + 0]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
+                        out.y = pack2<kBf16>(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+                        out.z = pack2<kBf16>(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
+                        out.w = pack2<kBf16>(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
+                        *reinterpret_cast<uint4*>(o_row + 2 * (c0 + i)) = out;
+                    }
+                }
+            }
+            tc_fence_before();
+        } else if (row_ok) {
+            // every key is masked for this whole block (causal, M > N): O = 0, L = -inf
+#pragma unroll
+            for (int c = 0; c < kD; c += 8) *reinterpret_cast<uint4*>(o_row + 2 * c) = make_uint4(0, 0, 0, 0);
+        }
+        if (row_ok) {
+            const float lse = (l_sum > 0.f) ? (m_ref + __logf(l_sum)) : -INFINITY;
+            p.lse[((int64_t)b * p.H + h) * p.M + grow] = lse;
+        }
+    }
+
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        tmem_dealloc<L::kTmemCols>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side launcher
+// ------------------------------------------------------------------------------------------
+template <int kD, bool kBf16, int kBiasMode, bool kCausal>
+static cudaError_t launch_fwd_inst(const AttnFwdKernelParams& kp, cudaStream_t stream) {
+    using L = FwdSmem<kD>;
+    auto kern = attn_fwd_kernel<kD, kBf16, kBiasMode, kCausal>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    if (e != cudaSuccess) return e;
+    const int grid = kp.B * kp.H * kp.num_m_blocks;
+    kern<<<grid, 256, L::kTotal, stream>>>(kp);
+    return cudaGetLastError();
+}
+
+template <int kD, bool kBf16>
+static cudaError_t launch_fwd_d(const AttnFwdKernelParams& kp, int bias_mode, bool causal, cudaStream_t stream) {
+    switch (bias_mode * 2 + (causal ? 1 : 0)) {
+        case 0: return launch_fwd_inst<kD, kBf16, 0, false>(kp, stream);
+        case 1: return launch_fwd_inst<kD, kBf16, 0, true>(kp, stream);
+        case 2: return launch_fwd_inst<kD, kBf16, 1, false>(kp, stream);
+        case 3: return launch_fwd_inst<kD, kBf16, 1, true>(kp, stream);
+        case 4: return launch_fwd_inst<kD, kBf16, 2, false>(kp, stream);
+        default: return launch_fwd_inst<kD, kBf16, 2, true>(kp, stream);
+    }
+}
+
+cudaError_t launch_attn_fwd(const AttnFwdKernelParams& kp, int D, bool bf16, int bias_mode, bool causal,
+                            cudaStream_t stream) {
+#define B200T5_FWD_CASE(DD)                                                              \
+    case DD:                                                                             \
+        return bf16 ? launch_fwd_d<DD, true>(kp, bias_mode, causal, stream)              \
+                    : launch_fwd_d<DD, false>(kp, bias_mode, causal, stream);
+    switch (D) {
+        B200T5_FWD_CASE(16)
+        B200T5_FWD_CASE(32)
+        B200T5_FWD_CASE(64)
+        B200T5_FWD_CASE(128)
+        default: return cudaErrorInvalidValue;
+    }
+#undef B200T5_FWD_CASE
+}
+
+}  // namespace b200t5

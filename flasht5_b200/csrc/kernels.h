@@ -1,0 +1,85 @@
+// Internal kernel-parameter blocks and launcher prototypes shared by the .cu files.
+// (The public C ABI is include/b200t5.h; nothing here is exported.)
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200t5 {
+
+struct AttnFwdKernelParams {
+    CUtensorMap map_q;      // (D, M, H, B)   box (min(D,64), 128, 1, 1)
+    CUtensorMap map_k;      // (D, N, H, B)
+    CUtensorMap map_v;      // (D, N, H, B)
+    CUtensorMap map_bias;   // (N, M, Hb, Bb) box (64, 128, 1, 1)            [bias mode 1]
+    const void* bias;       // raw pointer                                   [bias mode 2]
+    int64_t bias_sb, bias_sh, bias_sm, bias_sn;   // element strides          [bias mode 2]
+    void* o;
+    int64_t o_sb, o_sh, o_sm;                     // element strides, last dim contiguous
+    float* lse;             // (B, H, M) contiguous
+    int B, H, M, N;
+    int num_m_blocks;
+    int bias_b_bcast, bias_h_bcast;
+    float sm_scale;
+};
+
+struct AttnBwdKernelParams {
+    CUtensorMap map_q;      // (D, M, H, B)
+    CUtensorMap map_k;      // (D, N, H, B)
+    CUtensorMap map_v;      // (D, N, H, B)
+    CUtensorMap map_do;     // (D, M, H, B)
+    CUtensorMap map_bias;   // (N, M, Hb, Bb)                                 [bias mode 1]
+    CUtensorMap map_ds;     // (N, M, Hd, Bd) 16-bit dS destination           [bias mode 1]
+    CUtensorMap map_dq;     // fp32 accumulator (D, M, H, B), box (min(D,32), 128, 1, 1), reduce-add
+    const void* bias;       // [bias mode 2]
+    int64_t bias_sb, bias_sh, bias_sm, bias_sn;
+    void* ds;               // [bias mode 2] 16-bit dS destination
+    int64_t ds_sb, ds_sh, ds_sm, ds_sn;
+    void* dk;
+    int64_t dk_sb, dk_sh, dk_sn;
+    void* dv;
+    int64_t dv_sb, dv_sh, dv_sn;
+    const float* lse;       // (B, H, M)
+    const float* delta;     // (B, H, M)
+    int B, H, M, N;
+    int num_m_blocks, num_n_blocks;
+    int bias_b_bcast, bias_h_bcast;
+    float sm_scale;
+};
+
+cudaError_t launch_attn_fwd(const AttnFwdKernelParams& kp, int D, bool bf16, int bias_mode, bool causal,
+                            cudaStream_t stream);
+cudaError_t launch_attn_bwd(const AttnBwdKernelParams& kp, int D, bool bf16, int bias_mode, bool causal,
+                            cudaStream_t stream);
+
+// delta[b,h,m] = sum_d O*dO  (fp32); also zero-fills the fp32 dQ accumulator.
+cudaError_t launch_attn_bwd_preprocess(const void* o, const int64_t* o_strides, const void* dout,
+                                       const int64_t* do_strides, float* delta, float* dq_acc, int B, int H, int M,
+                                       int D, bool bf16, cudaStream_t stream);
+// dq[b,h,m,:] = 16bit(dq_acc * sm_scale)
+cudaError_t launch_attn_bwd_dq_convert(const float* dq_acc, void* dq, const int64_t* dq_strides, int B, int H, int M,
+                                       int D, float sm_scale, bool bf16, cudaStream_t stream);
+// dbias[bb,hb,m,n] = sum over broadcast batch/head of ds_ws[b,h,m,n]; causal-masked entries are 0 (never read).
+cudaError_t launch_dbias_reduce(const void* ds_ws, void* dbias, const int64_t* dbias_strides, int B, int H, int M,
+                                int N, int reduce_b, int reduce_h, bool causal, bool bf16, cudaStream_t stream);
+
+cudaError_t launch_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int rows, int n,
+                               int64_t x_row_stride, int64_t y_row_stride, float eps, int x_dtype, int w_dtype,
+                               cudaStream_t stream);
+cudaError_t launch_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx, void* dw,
+                               float* dw_partial, int num_partials, int rows, int n, int64_t dy_row_stride,
+                               int64_t x_row_stride, int64_t dx_row_stride, int x_dtype, int w_dtype,
+                               cudaStream_t stream);
+cudaError_t launch_ce_fwd(const void* logits, const int64_t* labels, float* losses, float* z_losses, float* lse,
+                          int rows, int vocab, int64_t row_stride, float smoothing, float logit_scale,
+                          float lse_square_scale, int64_t ignore_index, int dtype, cudaStream_t stream);
+cudaError_t launch_ce_bwd(const void* logits, const int64_t* labels, const float* lse, const float* dlosses,
+                          int64_t dloss_stride, void* dlogits, int rows, int vocab, int64_t row_stride,
+                          int64_t dlogits_row_stride, float smoothing, float logit_scale, float lse_square_scale,
+                          int64_t ignore_index, int dtype, cudaStream_t stream);
+
+// Launch counter (every kernel launched by this library bumps it; read through the C ABI).
+void count_launch(int n = 1);
+
+}  // namespace b200t5
