@@ -1,0 +1,404 @@
+// C ABI of libb200t5.so (declared in include/b200t5.h): argument validation, TMA tensor-map
+// construction from runtime strides, workspace carving and kernel launches.  No allocation, no
+// synchronisation, no CPU fallback.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/b200t5.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200t5 {
+
+// ------------------------------------------------------------------------------------------
+// error / bookkeeping
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void count_launch(int n) { g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed); }
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+static int fail_cuda(cudaError_t e, const char* what) {
+    return fail(B200T5_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+
+// RAII: make `device` current for the duration of a call
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != device) {
+            err = cudaSetDevice(device);
+            switched = err == cudaSuccess;
+        }
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+
+static int device_cc(int device, int* major) {
+    static std::mutex mu;
+    static int cache[64];
+    static bool have[64];
+    if (device < 0 || device >= 64) return fail(B200T5_ERR_INVALID, "device ordinal %d out of range", device);
+    std::lock_guard<std::mutex> lk(mu);
+    if (!have[device]) {
+        int mj = 0;
+        cudaError_t e = cudaDeviceGetAttribute(&mj, cudaDevAttrComputeCapabilityMajor, device);
+        if (e != cudaSuccess) return fail_cuda(e, "cudaDeviceGetAttribute");
+        cache[device] = mj;
+        have[device] = true;
+    }
+    *major = cache[device];
+    return 0;
+}
+
+static int require_sm100(int device) {
+    int mj = 0;
+    int rc = device_cc(device, &mj);
+    if (rc) return rc;
+    if (mj != 10)
+        return fail(B200T5_ERR_UNSUPPORTED, "device %d has compute capability %d.x; this library is sm_100a only", device,
+                    mj);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// TMA tensor maps
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+static CUtensorMapSwizzle swizzle_for_row_bytes(int row_bytes) {
+    return row_bytes >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                            : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// 4-D map over a (d3, d2, d1, d0) tensor; d0 innermost and contiguous.  `strides` are ELEMENT strides of
+// d1, d2, d3.  Size-1 dims get a synthetic (legal) stride.  box = (box0, box1, 1, 1).
+static int make_map_4d(CUtensorMap* map, const void* base, int elem_bytes, CUtensorMapDataType dt, uint64_t d0,
+                       uint64_t d1, uint64_t d2, uint64_t d3, int64_t s1, int64_t s2, int64_t s3, uint32_t box0,
+                       uint32_t box1, const char* what, bool swizzle_only_128 = false) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return fail(B200T5_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[4] = {d0, d1, d2, d3};
+    int64_t es[3] = {s1, s2, s3};
+    cuuint64_t strides[3];
+    uint64_t natural = d0 * static_cast<uint64_t>(elem_bytes);
+    for (int i = 0; i < 3; ++i) {
+        uint64_t sb = static_cast<uint64_t>(es[i]) * elem_bytes;
+        if (dims[i + 1] == 1 || es[i] <= 0) sb = (natural + 15) / 16 * 16;   // never dereferenced beyond index 0
+        if (sb % 16 != 0) return fail(B200T5_ERR_INVALID, "%s: stride %d (%lld elements) is not 16-byte aligned", what, i + 1, (long long)es[i]);
+        strides[i] = sb;
+        natural = sb * dims[i + 1];
+    }
+    if (reinterpret_cast<uintptr_t>(base) % 16 != 0) return fail(B200T5_ERR_INVALID, "%s: base pointer is not 16-byte aligned", what);
+    cuuint32_t box[4] = {box0, box1, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    const int row_bytes = static_cast<int>(box0) * elem_bytes;
+    const CUtensorMapSwizzle swz =
+        (swizzle_only_128 && row_bytes < 128) ? CU_TENSOR_MAP_SWIZZLE_NONE : swizzle_for_row_bytes(row_bytes);
+    CUresult r = enc(map, dt, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(B200T5_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed with CUresult %d", what, (int)r);
+    return 0;
+}
+
+static bool strides_tma_ok(const void* ptr, const int64_t* s, int b_dim, int h_dim) {
+    if (reinterpret_cast<uintptr_t>(ptr) % 16 != 0) return false;
+    if (s[3] != 1) return false;
+    if (s[2] % 8 != 0) return false;
+    if (h_dim > 1 && s[1] % 8 != 0) return false;
+    if (b_dim > 1 && s[0] % 8 != 0) return false;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// attention
+// ------------------------------------------------------------------------------------------
+static int validate_common(const b200t5_attn_params* p) {
+    if (!p) return fail(B200T5_ERR_INVALID, "params is NULL");
+    if (p->B < 1 || p->H < 1 || p->M < 1 || p->N < 1) return fail(B200T5_ERR_INVALID, "B, H, M, N must be >= 1 (got %d, %d, %d, %d)", p->B, p->H, p->M, p->N);
+    if (!(p->D == 16 || p->D == 32 || p->D == 64 || p->D == 128))
+        return fail(B200T5_ERR_UNSUPPORTED, "head dim %d not in {16, 32, 64, 128}", p->D);   // reference :233-234
+    if (!(p->dtype == B200T5_F16 || p->dtype == B200T5_BF16)) return fail(B200T5_ERR_UNSUPPORTED, "dtype %d is not fp16/bf16", p->dtype);
+    if (!p->q || !p->k || !p->v || !p->o || !p->lse) return fail(B200T5_ERR_INVALID, "q, k, v, o, lse must be non-NULL");
+    if (p->bias) {
+        if (!(p->bias_B == 1 || p->bias_B == p->B) || !(p->bias_H == 1 || p->bias_H == p->H))
+            return fail(B200T5_ERR_INVALID, "bias batch/head dims (%d, %d) must be 1 or (B, H) = (%d, %d)", p->bias_B, p->bias_H, p->B, p->H);
+    }
+    if ((int64_t)p->B * p->H * ((p->M + 127) / 128) > 0x7FFFFFFFLL || (int64_t)p->B * p->H * ((p->N + 127) / 128) > 0x7FFFFFFFLL)
+        return fail(B200T5_ERR_INVALID, "grid too large");
+    if (!strides_tma_ok(p->q, p->q_strides, p->B, p->H) || !strides_tma_ok(p->k, p->k_strides, p->B, p->H) ||
+        !strides_tma_ok(p->v, p->v_strides, p->B, p->H) || !strides_tma_ok(p->o, p->o_strides, p->B, p->H))
+        return fail(B200T5_ERR_INVALID, "q, k, v, o need unit last stride, 16-byte aligned base and other strides that are multiples of 8 elements");
+    return 0;
+}
+
+static int bias_mode_of(const b200t5_attn_params* p) {
+    if (!p->bias) return 0;
+    return strides_tma_ok(p->bias, p->bias_strides, p->bias_B, p->bias_H) ? 1 : 2;
+}
+
+static int round_up8(int x) { return (x + 7) / 8 * 8; }
+
+}  // namespace b200t5
+
+using namespace b200t5;
+
+extern "C" int b200t5_attn_fwd(const b200t5_attn_params* p) {
+    int rc = validate_common(p);
+    if (rc) return rc;
+    if ((rc = require_sm100(p->device))) return rc;
+    DeviceGuard guard(p->device);
+    if (guard.err != cudaSuccess) return fail_cuda(guard.err, "cudaSetDevice");
+
+    const CUtensorMapDataType dt = p->dtype == B200T5_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    const uint32_t boxd = p->D >= 64 ? 64 : p->D;
+    AttnFwdKernelParams kp;
+    memset(&kp, 0, sizeof(kp));
+    if ((rc = make_map_4d(&kp.map_q, p->q, 2, dt, p->D, p->M, p->H, p->B, p->q_strides[2], p->q_strides[1], p->q_strides[0], boxd, 128, "q"))) return rc;
+    if ((rc = make_map_4d(&kp.map_k, p->k, 2, dt, p->D, p->N, p->H, p->B, p->k_strides[2], p->k_strides[1], p->k_strides[0], boxd, 128, "k"))) return rc;
+    if ((rc = make_map_4d(&kp.map_v, p->v, 2, dt, p->D, p->N, p->H, p->B, p->v_strides[2], p->v_strides[1], p->v_strides[0], boxd, 128, "v"))) return rc;
+    const int mode = bias_mode_of(p);
+    if (mode == 1) {
+        if ((rc = make_map_4d(&kp.map_bias, p->bias, 2, dt, p->N, p->M, p->bias_H, p->bias_B, p->bias_strides[2], p->bias_strides[1], p->bias_strides[0], 64, 128, "bias"))) return rc;
+    } else if (mode == 2) {
+        kp.bias = p->bias;
+        kp.bias_sb = p->bias_strides[0];
+        kp.bias_sh = p->bias_strides[1];
+        kp.bias_sm = p->bias_strides[2];
+        kp.bias_sn = p->bias_strides[3];
+    }
+    kp.o = p->o;
+    kp.o_sb = p->o_strides[0];
+    kp.o_sh = p->o_strides[1];
+    kp.o_sm = p->o_strides[2];
+    kp.lse = p->lse;
+    kp.B = p->B; kp.H = p->H; kp.M = p->M; kp.N = p->N;
+    kp.num_m_blocks = (p->M + 127) / 128;
+    kp.bias_b_bcast = p->bias ? (p->bias_B == 1) : 1;
+    kp.bias_h_bcast = p->bias ? (p->bias_H == 1) : 1;
+    kp.sm_scale = p->sm_scale;
+    cudaError_t e = launch_attn_fwd(kp, p->D, p->dtype == B200T5_BF16, mode, p->causal != 0, static_cast<cudaStream_t>(p->stream));
+    if (e != cudaSuccess) return fail_cuda(e, "attn_fwd launch");
+    return 0;
+}
+
+namespace {
+struct BwdWorkspace {
+    size_t delta_off, dq_off, ds_off, total;
+    int n_pad;
+};
+BwdWorkspace bwd_workspace_layout(const b200t5_attn_params* p) {
+    BwdWorkspace w;
+    auto align = [](size_t x) { return (x + 255) / 256 * 256; };
+    const size_t rows = (size_t)p->B * p->H * p->M;
+    w.n_pad = round_up8(p->N);
+    w.delta_off = 0;
+    w.dq_off = align(rows * sizeof(float));
+    w.ds_off = w.dq_off + align(rows * p->D * sizeof(float));
+    w.total = w.ds_off + (p->bias ? align(rows * (size_t)w.n_pad * 2) : 0);
+    return w;
+}
+}  // namespace
+
+extern "C" size_t b200t5_attn_bwd_workspace_bytes(const b200t5_attn_params* p) {
+    if (!p || p->B < 1 || p->H < 1 || p->M < 1 || p->N < 1 || p->D < 1) return 0;
+    return bwd_workspace_layout(p).total;
+}
+
+extern "C" int b200t5_attn_bwd(const b200t5_attn_params* p) {
+    int rc = validate_common(p);
+    if (rc) return rc;
+    if (!p->dout || !p->dq || !p->dk || !p->dv) return fail(B200T5_ERR_INVALID, "dout, dq, dk, dv must be non-NULL");
+    if ((p->bias != nullptr) != (p->dbias != nullptr)) return fail(B200T5_ERR_INVALID, "dbias must be given exactly when bias is");
+    if (!strides_tma_ok(p->dout, p->do_strides, p->B, p->H) || !strides_tma_ok(p->dq, p->dq_strides, p->B, p->H) ||
+        !strides_tma_ok(p->dk, p->dk_strides, p->B, p->H) || !strides_tma_ok(p->dv, p->dv_strides, p->B, p->H))
+        return fail(B200T5_ERR_INVALID, "dout, dq, dk, dv need unit last stride, 16-byte aligned base and other strides that are multiples of 8 elements");
+    const BwdWorkspace w = bwd_workspace_layout(p);
+    if (!p->workspace || p->workspace_bytes < w.total) return fail(B200T5_ERR_WORKSPACE, "workspace of %zu bytes needed, %zu given", w.total, p->workspace ? p->workspace_bytes : (size_t)0);
+    if (reinterpret_cast<uintptr_t>(p->workspace) % 256 != 0) return fail(B200T5_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+    if ((rc = require_sm100(p->device))) return rc;
+    DeviceGuard guard(p->device);
+    if (guard.err != cudaSuccess) return fail_cuda(guard.err, "cudaSetDevice");
+
+    cudaStream_t stream = static_cast<cudaStream_t>(p->stream);
+    const bool bf16 = p->dtype == B200T5_BF16;
+    uint8_t* ws = static_cast<uint8_t*>(p->workspace);
+    float* delta = reinterpret_cast<float*>(ws + w.delta_off);
+    float* dq_acc = reinterpret_cast<float*>(ws + w.dq_off);
+    void* ds_ws = ws + w.ds_off;
+
+    cudaError_t e = launch_attn_bwd_preprocess(p->o, p->o_strides, p->dout, p->do_strides, delta, dq_acc, p->B, p->H, p->M, p->D, bf16, stream);
+    if (e != cudaSuccess) return fail_cuda(e, "attn_bwd_preprocess launch");
+
+    const CUtensorMapDataType dt = bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    const uint32_t boxd = p->D >= 64 ? 64 : p->D;
+    AttnBwdKernelParams kp;
+    memset(&kp, 0, sizeof(kp));
+    if ((rc = make_map_4d(&kp.map_q, p->q, 2, dt, p->D, p->M, p->H, p->B, p->q_strides[2], p->q_strides[1], p->q_strides[0], boxd, 128, "q"))) return rc;
+    if ((rc = make_map_4d(&kp.map_k, p->k, 2, dt, p->D, p->N, p->H, p->B, p->k_strides[2], p->k_strides[1], p->k_strides[0], boxd, 128, "k"))) return rc;
+    if ((rc = make_map_4d(&kp.map_v, p->v, 2, dt, p->D, p->N, p->H, p->B, p->v_strides[2], p->v_strides[1], p->v_strides[0], boxd, 128, "v"))) return rc;
+    if ((rc = make_map_4d(&kp.map_do, p->dout, 2, dt, p->D, p->M, p->H, p->B, p->do_strides[2], p->do_strides[1], p->do_strides[0], boxd, 128, "dout"))) return rc;
+    const uint32_t dqbox = p->D >= 32 ? 32 : p->D;
+    if ((rc = make_map_4d(&kp.map_dq, dq_acc, 4, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, p->D, p->M, p->H, p->B, p->D, (int64_t)p->M * p->D, (int64_t)p->H * p->M * p->D, dqbox, 128, "dq accumulator", true))) return rc;
+    const int mode = bias_mode_of(p);
+    if (mode == 1) {
+        if ((rc = make_map_4d(&kp.map_bias, p->bias, 2, dt, p->N, p->M, p->bias_H, p->bias_B, p->bias_strides[2], p->bias_strides[1], p->bias_strides[0], 64, 128, "bias"))) return rc;
+    } else if (mode == 2) {
+        kp.bias = p->bias;
+        kp.bias_sb = p->bias_strides[0];
+        kp.bias_sh = p->bias_strides[1];
+        kp.bias_sm = p->bias_strides[2];
+        kp.bias_sn = p->bias_strides[3];
+    }
+    if (mode != 0) {
+        // dS tiles always go to the (B, H, M, n_pad) 16-bit workspace through TMA stores
+        if ((rc = make_map_4d(&kp.map_ds, ds_ws, 2, dt, p->N, p->M, p->H, p->B, w.n_pad, (int64_t)p->M * w.n_pad, (int64_t)p->H * p->M * w.n_pad, 64, 128, "dS workspace"))) return rc;
+    }
+    kp.dk = p->dk; kp.dk_sb = p->dk_strides[0]; kp.dk_sh = p->dk_strides[1]; kp.dk_sn = p->dk_strides[2];
+    kp.dv = p->dv; kp.dv_sb = p->dv_strides[0]; kp.dv_sh = p->dv_strides[1]; kp.dv_sn = p->dv_strides[2];
+    kp.lse = p->lse;
+    kp.delta = delta;
+    kp.B = p->B; kp.H = p->H; kp.M = p->M; kp.N = p->N;
+    kp.num_m_blocks = (p->M + 127) / 128;
+    kp.num_n_blocks = (p->N + 127) / 128;
+    kp.bias_b_bcast = p->bias ? (p->bias_B == 1) : 1;
+    kp.bias_h_bcast = p->bias ? (p->bias_H == 1) : 1;
+    kp.sm_scale = p->sm_scale;
+    e = launch_attn_bwd(kp, p->D, bf16, mode, p->causal != 0, stream);
+    if (e != cudaSuccess) return fail_cuda(e, "attn_bwd launch");
+
+    e = launch_attn_bwd_dq_convert(dq_acc, p->dq, p->dq_strides, p->B, p->H, p->M, p->D, p->sm_scale, bf16, stream);
+    if (e != cudaSuccess) return fail_cuda(e, "attn_bwd_dq_convert launch");
+
+    if (mode != 0) {
+        e = launch_dbias_reduce(ds_ws, w.n_pad, p->dbias, p->dbias_strides, p->B, p->H, p->M, p->N, p->bias_B == 1, p->bias_H == 1, p->causal != 0, bf16, stream);
+        if (e != cudaSuccess) return fail_cuda(e, "dbias_reduce launch");
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// RMSNorm / cross-entropy
+// ------------------------------------------------------------------------------------------
+static int check_dtype3(int dt, const char* what) {
+    if (dt == B200T5_F16 || dt == B200T5_BF16 || dt == B200T5_F32) return 0;
+    return fail(B200T5_ERR_UNSUPPORTED, "%s dtype %d not in {fp16, bf16, fp32}", what, dt);
+}
+
+extern "C" int b200t5_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int64_t rows, int64_t n,
+                                  int64_t x_row_stride, int64_t y_row_stride, float eps, int x_dtype, int w_dtype,
+                                  int device, void* stream) {
+    if (!x || !w || !y || !rstd) return fail(B200T5_ERR_INVALID, "x, w, y, rstd must be non-NULL");
+    if (rows < 0 || n < 1 || n > 65536 || rows > 0x7FFFFFFF) return fail(B200T5_ERR_INVALID, "bad rows/n (%lld, %lld)", (long long)rows, (long long)n);
+    int rc;
+    if ((rc = check_dtype3(x_dtype, "x")) || (rc = check_dtype3(w_dtype, "w"))) return rc;
+    if ((rc = require_sm100(device))) return rc;
+    if (rows == 0) return 0;
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return fail_cuda(guard.err, "cudaSetDevice");
+    cudaError_t e = launch_rmsnorm_fwd(x, w, y, rstd, (int)rows, (int)n, x_row_stride, y_row_stride, eps, x_dtype, w_dtype, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail_cuda(e, "rmsnorm_fwd launch");
+    return 0;
+}
+
+extern "C" size_t b200t5_rmsnorm_bwd_workspace_bytes(int64_t n) {
+    if (n < 1) return 0;
+    return (size_t)kRmsnormMaxPartials * (size_t)n * sizeof(float);
+}
+
+extern "C" int b200t5_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx, void* dw,
+                                  void* workspace, size_t workspace_bytes, int64_t rows, int64_t n,
+                                  int64_t dy_row_stride, int64_t x_row_stride, int64_t dx_row_stride, int x_dtype,
+                                  int w_dtype, int device, void* stream) {
+    if (!dy || !x || !w || !rstd || !dx || !dw) return fail(B200T5_ERR_INVALID, "dy, x, w, rstd, dx, dw must be non-NULL");
+    if (rows < 0 || n < 1 || n > 65536 || rows > 0x7FFFFFFF) return fail(B200T5_ERR_INVALID, "bad rows/n (%lld, %lld)", (long long)rows, (long long)n);
+    int rc;
+    if ((rc = check_dtype3(x_dtype, "x")) || (rc = check_dtype3(w_dtype, "w"))) return rc;
+    const size_t need = b200t5_rmsnorm_bwd_workspace_bytes(n);
+    if (!workspace || workspace_bytes < need) return fail(B200T5_ERR_WORKSPACE, "workspace of %zu bytes needed", need);
+    if ((rc = require_sm100(device))) return rc;
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return fail_cuda(guard.err, "cudaSetDevice");
+    cudaError_t e = launch_rmsnorm_bwd(dy, x, w, rstd, dx, dw, static_cast<float*>(workspace), (int)rows, (int)n, dy_row_stride, x_row_stride, dx_row_stride, x_dtype, w_dtype, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail_cuda(e, "rmsnorm_bwd launch");
+    return 0;
+}
+
+extern "C" int b200t5_ce_fwd(const void* logits, const int64_t* labels, float* losses, float* z_losses, float* lse,
+                             int lse_is_input, int64_t rows, int64_t vocab, int64_t row_stride, float smoothing,
+                             float logit_scale, float lse_square_scale, int64_t ignore_index, int dtype, int device,
+                             void* stream) {
+    if (!logits || !labels || !losses || !z_losses || !lse) return fail(B200T5_ERR_INVALID, "logits, labels, losses, z_losses, lse must be non-NULL");
+    if (rows < 0 || vocab < 1 || rows > 0x7FFFFFFF || vocab > 0x7FFFFFFF) return fail(B200T5_ERR_INVALID, "bad rows/vocab");
+    if (lse_is_input && (smoothing != 0.f || logit_scale != 1.f)) return fail(B200T5_ERR_INVALID, "a precomputed lse needs smoothing == 0 and logit_scale == 1");
+    int rc;
+    if ((rc = check_dtype3(dtype, "logits"))) return rc;
+    if ((rc = require_sm100(device))) return rc;
+    if (rows == 0) return 0;
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return fail_cuda(guard.err, "cudaSetDevice");
+    cudaError_t e = launch_ce_fwd(logits, labels, losses, z_losses, lse, lse_is_input != 0, (int)rows, (int)vocab, row_stride, smoothing, logit_scale, lse_square_scale, ignore_index, dtype, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail_cuda(e, "ce_fwd launch");
+    return 0;
+}
+
+extern "C" int b200t5_ce_bwd(const void* logits, const int64_t* labels, const float* lse, const float* dlosses,
+                             int64_t dloss_stride, void* dlogits, int64_t rows, int64_t vocab, int64_t row_stride,
+                             int64_t dlogits_row_stride, float smoothing, float logit_scale, float lse_square_scale,
+                             int64_t ignore_index, int dtype, int device, void* stream) {
+    if (!logits || !labels || !lse || !dlosses || !dlogits) return fail(B200T5_ERR_INVALID, "logits, labels, lse, dlosses, dlogits must be non-NULL");
+    if (rows < 0 || vocab < 1 || rows > 0x7FFFFFFF || vocab > 0x7FFFFFFF) return fail(B200T5_ERR_INVALID, "bad rows/vocab");
+    int rc;
+    if ((rc = check_dtype3(dtype, "logits"))) return rc;
+    if ((rc = require_sm100(device))) return rc;
+    if (rows == 0) return 0;
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return fail_cuda(guard.err, "cudaSetDevice");
+    cudaError_t e = launch_ce_bwd(logits, labels, lse, dlosses, dloss_stride, dlogits, (int)rows, (int)vocab, row_stride, dlogits_row_stride, smoothing, logit_scale, lse_square_scale, ignore_index, dtype, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail_cuda(e, "ce_bwd launch");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// library state
+// ------------------------------------------------------------------------------------------
+extern "C" int b200t5_abi_version(void) { return B200T5_ABI_VERSION; }
+extern "C" const char* b200t5_last_error(void) { return g_err; }
+extern "C" uint64_t b200t5_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+extern "C" int b200t5_device_supported(int device) {
+    int mj = 0;
+    int rc = device_cc(device, &mj);
+    if (rc) return rc;
+    return mj == 10 ? 1 : 0;
+}

@@ -19,6 +19,8 @@
 //
 // TMEM columns: S [0,128) | dP [128,256) | dV [256,256+D) | dK [256+D,256+2D) | dQ [256+2D, 256+3D)
 // (D = 128: dQ aliases the S columns).
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -143,10 +145,8 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdKernelParams p) {
         tma_prefetch_desc(&p.map_v);
         tma_prefetch_desc(&p.map_do);
         tma_prefetch_desc(&p.map_dq);
-        if (kBiasMode == 1) {
-            tma_prefetch_desc(&p.map_bias);
-            tma_prefetch_desc(&p.map_ds);
-        }
+        if (kBiasMode == 1) tma_prefetch_desc(&p.map_bias);
+        if (kBiasMode != 0) tma_prefetch_desc(&p.map_ds);
     }
     tc_fence_before();
     __syncthreads();
@@ -393,17 +393,6 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdKernelParams p) {
                     *reinterpret_cast<uint4*>(sP + off) = make_uint4(pp[c8 * 4], pp[c8 * 4 + 1], pp[c8 * 4 + 2], pp[c8 * 4 + 3]);
                     *reinterpret_cast<uint4*>(sDS + off) = make_uint4(dd[c8 * 4], dd[c8 * 4 + 1], dd[c8 * 4 + 2], dd[c8 * 4 + 3]);
                 }
-                if (kBiasMode == 2) {
-                    // unaligned / odd-stride bias: dS goes out with plain 16-bit stores
-                    uint16_t* dp = reinterpret_cast<uint16_t*>(p.ds) + (int64_t)b * p.ds_sb + (int64_t)h * p.ds_sh +
-                                   (int64_t)grow * p.ds_sm;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int c = col0 + wg * 64 + ch * 32 + 2 * i;
-                        if (row_ok && c < p.N) dp[(int64_t)c * p.ds_sn] = static_cast<uint16_t>(dd[i] & 0xFFFFu);
-                        if (row_ok && c + 1 < p.N) dp[(int64_t)(c + 1) * p.ds_sn] = static_cast<uint16_t>(dd[i] >> 16);
-                    }
-                }
             }
             if (kBiasMode == 1) {
                 __syncwarp();
@@ -413,7 +402,7 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdKernelParams p) {
             named_bar_sync(1, 256);
             if (ctid == 0) {
                 mbar_arrive(pds_full);
-                if (kBiasMode == 1) {
+                if (kBiasMode != 0) {
                     tma_store_4d(&p.map_ds, smem + C::kDS, col0, mrow0, h, b);
                     tma_store_4d(&p.map_ds, smem + C::kDS + kHalfBytes, col0 + 64, mrow0, h, b);
                     bulk_commit_group();
@@ -576,10 +565,11 @@ __global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ dq_acc, uin
 // dBias = sum of the per-(batch, head) dS tiles over every broadcast dimension, fp32 accumulation,
 // one rounding (reference: ds.sum(0) :214-215; the head sum is the fix described in SURVEY.md section 4).
 template <bool kBf16>
-__global__ void dbias_reduce_kernel(const uint16_t* __restrict__ ws, uint16_t* __restrict__ out, int64_t o_sb,
-                                    int64_t o_sh, int64_t o_sm, int64_t o_sn, int B, int H, int M, int N, int reduce_b,
-                                    int reduce_h, int causal) {
+__global__ void dbias_reduce_kernel(const uint16_t* __restrict__ ws, int pitch, uint16_t* __restrict__ out,
+                                    int64_t o_sb, int64_t o_sh, int64_t o_sm, int64_t o_sn, int B, int H, int M, int N,
+                                    int reduce_b, int reduce_h, int causal) {
     const int64_t mn = (int64_t)M * N;
+    const int64_t mp = (int64_t)M * pitch;
     const int ob_n = reduce_b ? 1 : B;
     const int oh_n = reduce_h ? 1 : H;
     const int64_t total = (int64_t)ob_n * oh_n * mn;
@@ -597,7 +587,7 @@ __global__ void dbias_reduce_kernel(const uint16_t* __restrict__ ws, uint16_t* _
             const int h0 = reduce_h ? 0 : oh, h1 = reduce_h ? H : oh + 1;
             for (int bb = b0; bb < b1; ++bb)
                 for (int hh = h0; hh < h1; ++hh)
-                    acc += to_float16bit<kBf16>(ws[((int64_t)bb * H + hh) * mn + (int64_t)m * N + n]);
+                    acc += to_float16bit<kBf16>(ws[((int64_t)bb * H + hh) * mp + (int64_t)m * pitch + n]);
         }
         const uint32_t packed = pack2<kBf16>(acc, 0.f);
         out[ob * o_sb + oh * o_sh + m * o_sm + n * o_sn] = static_cast<uint16_t>(packed & 0xFFFFu);
@@ -606,10 +596,11 @@ __global__ void dbias_reduce_kernel(const uint16_t* __restrict__ ws, uint16_t* _
 
 // 8 columns per thread (16-byte loads), N % 8 == 0 and contiguous output rows
 template <bool kBf16>
-__global__ void dbias_reduce_vec8_kernel(const uint4* __restrict__ ws, uint4* __restrict__ out, int B, int H, int M,
-                                         int N, int reduce_b, int reduce_h, int causal) {
+__global__ void dbias_reduce_vec8_kernel(const uint4* __restrict__ ws, int pitch8, uint4* __restrict__ out, int B,
+                                         int H, int M, int N, int reduce_b, int reduce_h, int causal) {
     const int n8 = N / 8;
     const int64_t mn8 = (int64_t)M * n8;
+    const int64_t mp8 = (int64_t)M * pitch8;
     const int ob_n = reduce_b ? 1 : B;
     const int oh_n = reduce_h ? 1 : H;
     const int64_t total = (int64_t)ob_n * oh_n * mn8;
@@ -630,7 +621,7 @@ __global__ void dbias_reduce_vec8_kernel(const uint4* __restrict__ ws, uint4* __
             const int h0 = reduce_h ? 0 : oh, h1 = reduce_h ? H : oh + 1;
             for (int bb = b0; bb < b1; ++bb)
                 for (int hh = h0; hh < h1; ++hh) {
-                    const uint4 u = __ldg(ws + ((int64_t)bb * H + hh) * mn8 + (int64_t)m * n8 + c8);
+                    const uint4 u = __ldg(ws + ((int64_t)bb * H + hh) * mp8 + (int64_t)m * pitch8 + c8);
                     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -663,6 +654,7 @@ static cudaError_t launch_bwd_inst(const AttnBwdKernelParams& kp, cudaStream_t s
     if (e != cudaSuccess) return e;
     const int grid = kp.B * kp.H * kp.num_n_blocks;
     kern<<<grid, 384, C::kTotal, stream>>>(kp);
+    count_launch();
     return cudaGetLastError();
 }
 
@@ -712,6 +704,7 @@ cudaError_t launch_attn_bwd_preprocess(const void* o, const int64_t* os, const v
         default: return cudaErrorInvalidValue;
     }
 #undef B200T5_PRE
+    count_launch();
     return cudaGetLastError();
 }
 
@@ -731,11 +724,12 @@ cudaError_t launch_attn_bwd_dq_convert(const float* dq_acc, void* dq, const int6
         default: return cudaErrorInvalidValue;
     }
 #undef B200T5_CVT
+    count_launch();
     return cudaGetLastError();
 }
 
-cudaError_t launch_dbias_reduce(const void* ds_ws, void* dbias, const int64_t* s, int B, int H, int M, int N,
-                                int reduce_b, int reduce_h, bool causal, bool bf16, cudaStream_t stream) {
+cudaError_t launch_dbias_reduce(const void* ds_ws, int ws_pitch, void* dbias, const int64_t* s, int B, int H, int M,
+                                int N, int reduce_b, int reduce_h, bool causal, bool bf16, cudaStream_t stream) {
     const int ob = reduce_b ? 1 : B, oh = reduce_h ? 1 : H;
     const bool contiguous = s[3] == 1 && s[2] == N && (oh == 1 || s[1] == (int64_t)M * N) &&
                             (ob == 1 || s[0] == (int64_t)oh * M * N);
@@ -746,25 +740,26 @@ cudaError_t launch_dbias_reduce(const void* ds_ws, void* dbias, const int64_t* s
         const int64_t total = (int64_t)ob * oh * M * (N / 8);
         const int grid = static_cast<int>(std::min<int64_t>((total + block - 1) / block, 148 * 16));
         if (bf16)
-            dbias_reduce_vec8_kernel<true><<<grid, block, 0, stream>>>(static_cast<const uint4*>(ds_ws),
+            dbias_reduce_vec8_kernel<true><<<grid, block, 0, stream>>>(static_cast<const uint4*>(ds_ws), ws_pitch / 8,
                                                                        static_cast<uint4*>(dbias), B, H, M, N,
                                                                        reduce_b, reduce_h, causal ? 1 : 0);
         else
-            dbias_reduce_vec8_kernel<false><<<grid, block, 0, stream>>>(static_cast<const uint4*>(ds_ws),
+            dbias_reduce_vec8_kernel<false><<<grid, block, 0, stream>>>(static_cast<const uint4*>(ds_ws), ws_pitch / 8,
                                                                         static_cast<uint4*>(dbias), B, H, M, N,
                                                                         reduce_b, reduce_h, causal ? 1 : 0);
     } else {
         const int64_t total = (int64_t)ob * oh * M * N;
         const int grid = static_cast<int>(std::min<int64_t>((total + block - 1) / block, 148 * 16));
         if (bf16)
-            dbias_reduce_kernel<true><<<grid, block, 0, stream>>>(static_cast<const uint16_t*>(ds_ws),
+            dbias_reduce_kernel<true><<<grid, block, 0, stream>>>(static_cast<const uint16_t*>(ds_ws), ws_pitch,
                                                                   static_cast<uint16_t*>(dbias), s[0], s[1], s[2],
                                                                   s[3], B, H, M, N, reduce_b, reduce_h, causal ? 1 : 0);
         else
-            dbias_reduce_kernel<false><<<grid, block, 0, stream>>>(static_cast<const uint16_t*>(ds_ws),
+            dbias_reduce_kernel<false><<<grid, block, 0, stream>>>(static_cast<const uint16_t*>(ds_ws), ws_pitch,
                                                                    static_cast<uint16_t*>(dbias), s[0], s[1], s[2],
                                                                    s[3], B, H, M, N, reduce_b, reduce_h, causal ? 1 : 0);
     }
+    count_launch();
     return cudaGetLastError();
 }
 

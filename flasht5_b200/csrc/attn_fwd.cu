@@ -437,6 +437,7 @@ static cudaError_t launch_fwd_inst(const AttnFwdKernelParams& kp, cudaStream_t s
     if (e != cudaSuccess) return e;
     const int grid = kp.B * kp.H * kp.num_m_blocks;
     kern<<<grid, 256, L::kTotal, stream>>>(kp);
+    count_launch();
     return cudaGetLastError();
 }
 

@@ -75,31 +75,49 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
-#ifndef B200T5_SPIN_LIMIT
-#define B200T5_SPIN_LIMIT (1u << 26)   // ~seconds; converts a protocol deadlock into a trap
+// A protocol deadlock (a barrier that never completes) becomes a trap after this many nanoseconds
+// instead of hanging the GPU; 0 disables the watchdog.
+#ifndef B200T5_WATCHDOG_NS
+#define B200T5_WATCHDOG_NS 4000000000ull
 #endif
 
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    uint32_t done = 0;
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ bool mbar_try_wait(uint32_t addr, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+
+static __device__ __noinline__ void mbar_wait_slow(uint32_t addr, uint32_t parity) {
+    const uint64_t t0 = globaltimer_ns();
     uint32_t spins = 0;
-    while (true) {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}\n"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-        if (done) break;
-        if (++spins > B200T5_SPIN_LIMIT) {
+    while (!mbar_try_wait(addr, parity)) {
+        if (B200T5_WATCHDOG_NS != 0 && (++spins & 0xFFu) == 0 && globaltimer_ns() - t0 > B200T5_WATCHDOG_NS) {
             printf("b200t5: mbarrier deadlock block(%d,%d,%d) thread %d bar@%u parity %u\n", blockIdx.x, blockIdx.y,
                    blockIdx.z, threadIdx.x, addr, parity);
             __trap();
         }
     }
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    if (mbar_try_wait(addr, parity)) return;
+    if (mbar_try_wait(addr, parity)) return;
+    mbar_wait_slow(addr, parity);
 }
 
 // ------------------------------------------------------------------------------------------

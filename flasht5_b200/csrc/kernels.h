@@ -30,12 +30,10 @@ struct AttnBwdKernelParams {
     CUtensorMap map_v;      // (D, N, H, B)
     CUtensorMap map_do;     // (D, M, H, B)
     CUtensorMap map_bias;   // (N, M, Hb, Bb)                                 [bias mode 1]
-    CUtensorMap map_ds;     // (N, M, Hd, Bd) 16-bit dS destination           [bias mode 1]
+    CUtensorMap map_ds;     // (N, M, H, B) 16-bit dS workspace, row pitch = N rounded up to 8   [bias modes 1, 2]
     CUtensorMap map_dq;     // fp32 accumulator (D, M, H, B), box (min(D,32), 128, 1, 1), reduce-add
     const void* bias;       // [bias mode 2]
     int64_t bias_sb, bias_sh, bias_sm, bias_sn;
-    void* ds;               // [bias mode 2] 16-bit dS destination
-    int64_t ds_sb, ds_sh, ds_sm, ds_sn;
     void* dk;
     int64_t dk_sb, dk_sh, dk_sn;
     void* dv;
@@ -61,18 +59,18 @@ cudaError_t launch_attn_bwd_preprocess(const void* o, const int64_t* o_strides, 
 cudaError_t launch_attn_bwd_dq_convert(const float* dq_acc, void* dq, const int64_t* dq_strides, int B, int H, int M,
                                        int D, float sm_scale, bool bf16, cudaStream_t stream);
 // dbias[bb,hb,m,n] = sum over broadcast batch/head of ds_ws[b,h,m,n]; causal-masked entries are 0 (never read).
-cudaError_t launch_dbias_reduce(const void* ds_ws, void* dbias, const int64_t* dbias_strides, int B, int H, int M,
-                                int N, int reduce_b, int reduce_h, bool causal, bool bf16, cudaStream_t stream);
+cudaError_t launch_dbias_reduce(const void* ds_ws, int ws_pitch, void* dbias, const int64_t* dbias_strides, int B, int H,
+                                int M, int N, int reduce_b, int reduce_h, bool causal, bool bf16, cudaStream_t stream);
 
 cudaError_t launch_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int rows, int n,
                                int64_t x_row_stride, int64_t y_row_stride, float eps, int x_dtype, int w_dtype,
                                cudaStream_t stream);
+constexpr int kRmsnormMaxPartials = 296;   // 2 CTAs per SM x 148 SMs: rows of the fp32 partial-dW workspace
 cudaError_t launch_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx, void* dw,
-                               float* dw_partial, int num_partials, int rows, int n, int64_t dy_row_stride,
-                               int64_t x_row_stride, int64_t dx_row_stride, int x_dtype, int w_dtype,
-                               cudaStream_t stream);
+                               float* dw_partial, int rows, int n, int64_t dy_row_stride, int64_t x_row_stride,
+                               int64_t dx_row_stride, int x_dtype, int w_dtype, cudaStream_t stream);
 cudaError_t launch_ce_fwd(const void* logits, const int64_t* labels, float* losses, float* z_losses, float* lse,
-                          int rows, int vocab, int64_t row_stride, float smoothing, float logit_scale,
+                          bool lse_is_input, int rows, int vocab, int64_t row_stride, float smoothing, float logit_scale,
                           float lse_square_scale, int64_t ignore_index, int dtype, cudaStream_t stream);
 cudaError_t launch_ce_bwd(const void* logits, const int64_t* labels, const float* lse, const float* dlosses,
                           int64_t dloss_stride, void* dlogits, int rows, int vocab, int64_t row_stride,

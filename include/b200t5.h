@@ -1,0 +1,139 @@
+/*
+ * b200t5 -- C ABI of the B200-native (sm_100a) replacement for the hot path of catie-aq/flashT5.
+ *
+ * One shared library (libb200t5.so), plain pointers and sizes, no torch types.  Every entry point
+ * is what the reference's Python launcher for that kernel would bind through ctypes (see
+ * INTEGRATION.md).  Citations are relative to the reference checkout.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers on `device`; the library never allocates, frees or
+ *     synchronises; every kernel is enqueued on `stream` (a cudaStream_t passed as void*);
+ *     workspaces are caller-allocated (query the size first); entry points are CUDA-graph safe.
+ *   - strides are in ELEMENTS, order (batch, head, seq, dim); the last (dim) stride must be 1.
+ *   - return value: 0 on success, a negative B200T5_ERR_* code otherwise; the message is kept in
+ *     thread-local storage and returned by b200t5_last_error().
+ *   - there is NO CPU fallback: with no sm_100 device every compute entry point fails with
+ *     B200T5_ERR_CUDA / B200T5_ERR_UNSUPPORTED.
+ */
+#ifndef B200T5_H_
+#define B200T5_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200T5_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define B200T5_API __attribute__((visibility("default")))
+#else
+#define B200T5_API
+#endif
+
+enum {
+    B200T5_OK = 0,
+    B200T5_ERR_INVALID = -1,     /* bad shape / stride / pointer alignment / null pointer          */
+    B200T5_ERR_UNSUPPORTED = -2, /* dtype or head dim outside {fp16,bf16} x {16,32,64,128}, non sm_100 device */
+    B200T5_ERR_CUDA = -3,        /* a CUDA runtime / driver call or kernel launch failed             */
+    B200T5_ERR_WORKSPACE = -4    /* workspace missing or too small                                   */
+};
+
+enum { B200T5_F16 = 0, B200T5_BF16 = 1, B200T5_F32 = 2 };
+
+/* ------------------------------------------------------------------------------------------------
+ * Attention with additive bias.
+ * Replaces torch.ops.flasht5.flash_attn_v2_fwd / _bwd and their Triton kernels
+ *   src/model/ops/flash_attention_v2_bias.py:27-80 (fwd launcher), :327-483 (_fwd_kernel),
+ *   :91-217 (bwd launcher), :516-556 (_bwd_preprocess), :559-745 (_bwd_kv_kernel),
+ *   :748-905 (_bwd_q_kernel), :214-215 (ds.sum(0)).
+ *
+ * q:(B,H,M,D)  k,v:(B,H,N,D)  bias:(bias_B,bias_H,M,N) with bias_B in {1,B}, bias_H in {1,H},
+ * or bias == NULL (cross attention).  o has q's shape; lse:(B,H,M) fp32 contiguous.
+ * Semantics: S = sm_scale * Q K^T + bias, bottom-right aligned causal
+ * mask (visible iff n <= m + N - M), lse = ln sum exp S (natural log), rows with no visible key
+ * give o = 0 and lse = -inf.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct b200t5_attn_params {
+    /* problem */
+    int32_t B, H, M, N, D;
+    int32_t dtype;        /* B200T5_F16 | B200T5_BF16: q,k,v,bias,o,do,dq,dk,dv,dbias all share it */
+    int32_t causal;       /* 0 | 1 */
+    int32_t bias_B;       /* 1 or B  (ignored when bias == NULL) */
+    int32_t bias_H;       /* 1 or H */
+    float sm_scale;
+    int32_t device;       /* CUDA device ordinal the pointers live on */
+    int32_t reserved0;
+    void* stream;         /* cudaStream_t */
+
+    /* forward operands */
+    const void* q;  int64_t q_strides[4];
+    const void* k;  int64_t k_strides[4];
+    const void* v;  int64_t v_strides[4];
+    const void* bias; int64_t bias_strides[4];   /* strides of the size-1 dims are ignored */
+    void* o;        int64_t o_strides[4];        /* fwd: output; bwd: input */
+    float* lse;                                   /* fwd: output; bwd: input */
+
+    /* backward operands (ignored by b200t5_attn_fwd) */
+    const void* dout; int64_t do_strides[4];
+    void* dq;       int64_t dq_strides[4];
+    void* dk;       int64_t dk_strides[4];
+    void* dv;       int64_t dv_strides[4];
+    void* dbias;    int64_t dbias_strides[4];    /* bias's shape; NULL iff bias == NULL */
+    void* workspace;                              /* >= b200t5_attn_bwd_workspace_bytes() bytes, 256-B aligned */
+    size_t workspace_bytes;
+} b200t5_attn_params;
+
+B200T5_API int b200t5_attn_fwd(const b200t5_attn_params* p);
+B200T5_API size_t b200t5_attn_bwd_workspace_bytes(const b200t5_attn_params* p);
+B200T5_API int b200t5_attn_bwd(const b200t5_attn_params* p);
+
+/* ------------------------------------------------------------------------------------------------
+ * RMSNorm.  Replaces torch.ops.flasht5.rmsnorm_triton_fwd / _bwd
+ *   src/model/ops/rms_norm.py:134-174 (+ kernel :25-66), :186-236 (+ kernel :68-131).
+ * x, y, dy, dx: (rows, n) with unit last stride; w, dw: (n); rstd: (rows) fp32.
+ * x_dtype / w_dtype: B200T5_F16 | B200T5_BF16 | B200T5_F32 (y, dy, dx use x_dtype; dw uses w_dtype).
+ * bwd needs a workspace of b200t5_rmsnorm_bwd_workspace_bytes(n) bytes (fp32 partial dW rows).
+ * ---------------------------------------------------------------------------------------------- */
+B200T5_API int b200t5_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int64_t rows, int64_t n,
+                       int64_t x_row_stride, int64_t y_row_stride, float eps, int x_dtype, int w_dtype,
+                       int device, void* stream);
+B200T5_API size_t b200t5_rmsnorm_bwd_workspace_bytes(int64_t n);
+B200T5_API int b200t5_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx, void* dw,
+                       void* workspace, size_t workspace_bytes, int64_t rows, int64_t n, int64_t dy_row_stride,
+                       int64_t x_row_stride, int64_t dx_row_stride, int x_dtype, int w_dtype, int device,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Cross-entropy + z-loss.  Replaces torch.ops.flasht5.cross_entropy_triton_fwd / _bwd
+ *   src/model/ops/cross_entropy_loss.py:164-217 (+ kernel :40-111), :228-274 (+ kernel :119-162).
+ * logits: (rows, vocab) unit last stride, dtype in {F16,BF16,F32}; labels: (rows) int64;
+ * losses, z_losses, lse: (rows) fp32.  lse_is_input != 0: `lse` holds a precomputed log-sum-exp that is
+ * used instead of being recomputed (reference PRECOMPUTED_LSE, :66-76; requires smoothing == 0 and
+ * logit_scale == 1).  dlogits may alias logits (in-place backward).
+ * dlosses: (rows) fp32 with element stride dloss_stride.
+ * ---------------------------------------------------------------------------------------------- */
+B200T5_API int b200t5_ce_fwd(const void* logits, const int64_t* labels, float* losses, float* z_losses, float* lse,
+                  int lse_is_input, int64_t rows, int64_t vocab, int64_t row_stride, float smoothing,
+                  float logit_scale, float lse_square_scale, int64_t ignore_index, int dtype, int device,
+                  void* stream);
+B200T5_API int b200t5_ce_bwd(const void* logits, const int64_t* labels, const float* lse, const float* dlosses,
+                  int64_t dloss_stride, void* dlogits, int64_t rows, int64_t vocab, int64_t row_stride,
+                  int64_t dlogits_row_stride, float smoothing, float logit_scale, float lse_square_scale,
+                  int64_t ignore_index, int dtype, int device, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Library state
+ * ---------------------------------------------------------------------------------------------- */
+B200T5_API int b200t5_abi_version(void);
+B200T5_API const char* b200t5_last_error(void);          /* thread-local, never NULL */
+B200T5_API uint64_t b200t5_launch_count(void);           /* kernels launched by this library since load (all threads) */
+/* 1 if `device` is an sm_100 part this library can run on, 0 otherwise, negative on CUDA error */
+B200T5_API int b200t5_device_supported(int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200T5_H_ */
