@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: FlashAttention-2 with additive T5 bias, forward + backward (dQ, dK, dV,
+dBias), bf16, S = 1024 -- the metric BASELINE.json names.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+One "step" = one forward + one backward pass of the operator over one batch of synthetic inputs.
+Per-GPU workload (weak scaling): B=32, H=8, M=N=1024, D=64, bias (1,H,M,N): the per-GPU shape of
+BASELINE.json configs[4] (FAT5-small, S=1024), which is the S=1024 shape the metric is quoted on.
+FLOP convention = the reference benchmark's (benchmarks/bench_fa2_bias.py:10-13): fwd 4*B*H*M*N*D,
+bwd 2.5x, fwd+bwd 3.5x.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "attention TFLOP/s fwd+bwd bf16 S=1024"
+UNIT = "TFLOP/s"
+# per-GPU workload
+WB, WH, WS, WD = 32, 8, 1024, 64
+SM_SCALE = 1.0                      # the reference's shipped configs use attention_scale 1.0
+WORKLOAD = ("FAT5-small encoder self-attention fwd+bwd (dQ,dK,dV,dBias), per-GPU B=%d H=%d S=%d d=%d, "
+            "bias (1,H,S,S), non-causal, sm_scale=1.0 (BASELINE.json configs[4] per-GPU shape)" % (WB, WH, WS, WD))
+
+
+def flops_fwd(B, H, M, N, D, causal=False):
+    return 4.0 * B * H * M * N * D / (2.0 if causal else 1.0)
+
+
+def flops_fwd_bwd(B, H, M, N, D, causal=False):
+    return 3.5 * flops_fwd(B, H, M, N, D, causal)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            pk = json.load(f)
+        return float(pk["bf16_tflops"]), "measured burst (MEASURED_PEAKS.json bf16_tflops)"
+    except Exception:   # noqa: BLE001
+        return 1590.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s)"
+
+
+def load_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get("attn_bwd_kernel_dram_bytes_per_launch")
+    except Exception:   # noqa: BLE001
+        return None
+
+
+class ClockSampler:
+    """Samples nvidia-smi during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:   # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:   # noqa: BLE001
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+                power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(smax), "power_w_max": max(power), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's eager attention-with-bias (src/utils/attn_ref.py,
+# restated in oracle/attn_bias_ref.py:attn_eager_lowp) + torch autograd on the host CPU cores.
+# This is the ONLY place bench.py executes anything under oracle/.
+# ---------------------------------------------------------------------------------------------
+def cpu_eager_attention(sample_b: int, iters: int, warmup: int):
+    import torch
+    from oracle import attn_bias_ref as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(1234)
+    mk = lambda s: torch.randn(sample_b, s, WH, WD, generator=g).to(torch.bfloat16).permute(0, 2, 1, 3)  # noqa: E731
+    q, k, v, do = mk(WS), mk(WS), mk(WS), mk(WS)
+    bias = torch.randn(1, WH, WS, WS, generator=g).to(torch.bfloat16)
+    for t in (q, k, v, bias):
+        t.requires_grad_(True)
+    times = []
+    t_begin = time.perf_counter()
+    for i in range(warmup + iters):
+        t0 = time.perf_counter()
+        o = orc.attn_eager_lowp(q, k, v, bias, False, SM_SCALE)
+        torch.autograd.grad(o, (q, k, v, bias), do)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+        if times and time.perf_counter() - t_begin > 25.0:      # bounded: ~10-30 s of CPU work
+            break
+    iters = len(times)
+    sec = sum(times) / len(times)
+    tf = flops_fwd_bwd(sample_b, WH, WS, WS, WD) / sec / 1e12
+    sample = ("B=%d of the per-GPU B=%d (same H=%d S=%d d=%d, bias (1,H,S,S)), %d warm-up + %d timed fwd+bwd "
+              "iterations of the reference's eager bf16 attention (attn_ref semantics) + torch autograd, %d threads"
+              % (sample_b, WB, WH, WS, WD, warmup, iters, cores))
+    return tf, sec, cores, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    iters = max(1, min(args.steps, 10))
+    warm = max(1, min(args.warmup, 2))
+    tf, sec, cores, sample = cpu_eager_attention(sample_b=8, iters=iters, warmup=warm)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": tf, "unit": UNIT, "n_gpus": args.gpus, "steps": iters,
+        "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "reference arm = the reference's eager PyTorch attention-with-bias on "
+                   "the host CPU (oracle port of src/utils/attn_ref.py; the reference is pure Python and cannot be "
+                   "compiled or shipped); each step is a bounded sample of the workload"},
+        "cpu_baseline": {"value": tf, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": tf, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from flasht5_b200 import _cabi, flash_attention_v2_bias
+    from flasht5_b200.data_parallel import allreduce_dbias
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs the torchrun launch described in the docstring" % args.gpus)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl ours) needs a B200: there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _cabi.load()
+    if lib.b200t5_device_supported(local_rank) != 1:
+        raise SystemExit("device is not sm_100: " + _cabi.last_error())
+
+    B, H, S, D = WB, WH, WS, WD
+    dtype = torch.bfloat16
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    # The model's layout: (B, S, H, D) memory viewed as (B, H, S, D)  (modeling_flash_t5.py:281-283).
+    # Three rotating input sets (3 x 185 MB > 126 MB L2) so no step finds its inputs in L2.
+    NSETS = 3
+
+    def mk():
+        return torch.randn(B, S, H, D, generator=g, device=dev, dtype=torch.float32).to(dtype).permute(0, 2, 1, 3)
+    sets = []
+    for _ in range(NSETS):
+        q, k, v, do = mk(), mk(), mk(), mk()
+        bias = (0.5 * torch.randn(1, H, S, S, generator=g, device=dev)).to(dtype)
+        sets.append((q, k, v, bias, do))
+    F_step = flops_fwd_bwd(B, H, S, S, D)
+
+    def step(i):
+        q, k, v, bias, do = sets[i % NSETS]
+        o, L = torch.ops.b200t5.attn_bias_fwd(q, k, v, bias, False, SM_SCALE)
+        dq, dk, dv, ds = torch.ops.b200t5.attn_bias_bwd(o, do, q, k, v, bias, L, False, SM_SCALE)
+        if world > 1:
+            ds = allreduce_dbias(ds)
+        return o, dq, dk, dv, ds
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    _cabi.profile_enable(True)
+    _cabi.profile_collect()
+    launches0 = _cabi.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        step(i)
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = _cabi.launch_count() - launches0
+    prof = _cabi.profile_collect()
+    _cabi.profile_enable(False)
+    clocks = sampler.stop() if sampler else None
+
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * F_step / (ms_step * 1e-3) / 1e12
+
+    # ---- roofline of the dominant kernel (the fused backward), live CUDA-event times ----
+    bwd_ms = [ms for kid, ms in prof if kid == 2 and ms > 0]
+    fwd_ms = [ms for kid, ms in prof if kid == 1 and ms > 0]
+    peak, peak_src = load_peaks()
+    roofline = None
+    if bwd_ms:
+        avg = sum(bwd_ms) / len(bwd_ms)
+        ach = 2.5 * flops_fwd(B, H, S, S, D) / (avg * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "attn_bwd_kernel (fused dQ/dK/dV/dS)", "achieved": ach, "peak": peak,
+                    "unit": "TFLOP/s", "frac": ach / peak, "traffic": load_traffic(), "peak_source": peak_src,
+                    "avg_launch_ms": avg, "launches_timed": len(bwd_ms),
+                    "algorithmic_flops_per_launch": 2.5 * flops_fwd(B, H, S, S, D)}
+        if fwd_ms:
+            favg = sum(fwd_ms) / len(fwd_ms)
+            fach = flops_fwd(B, H, S, S, D) / (favg * 1e-3) / 1e12
+            roofline["fwd_kernel"] = {"achieved": fach, "frac": fach / peak, "avg_launch_ms": favg}
+
+    # ---- e2e: host buffers -> public autograd API -> host results, copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        hq, hk, hv, hb, hdo = (x.detach().cpu().contiguous().pin_memory() for x in
+                               (sets[0][0].permute(0, 2, 1, 3), sets[0][1].permute(0, 2, 1, 3),
+                                sets[0][2].permute(0, 2, 1, 3), sets[0][3], sets[0][4].permute(0, 2, 1, 3)))
+        outs_h = [torch.empty_like(hq).pin_memory() for _ in range(4)] + [torch.empty_like(hb).pin_memory()]
+        h2d = sum(x.numel() * x.element_size() for x in (hq, hk, hv, hb, hdo))
+        d2h = sum(x.numel() * x.element_size() for x in outs_h)
+
+        def e2e_step():
+            q = hq.to(dev, non_blocking=True).permute(0, 2, 1, 3).requires_grad_(True)
+            k = hk.to(dev, non_blocking=True).permute(0, 2, 1, 3).requires_grad_(True)
+            v = hv.to(dev, non_blocking=True).permute(0, 2, 1, 3).requires_grad_(True)
+            b = hb.to(dev, non_blocking=True).requires_grad_(True)
+            do = hdo.to(dev, non_blocking=True).permute(0, 2, 1, 3)
+            o = flash_attention_v2_bias(q, k, v, b, False, SM_SCALE)
+            dq, dk, dv, db = torch.autograd.grad(o, (q, k, v, b), do)
+            if world > 1:
+                db = allreduce_dbias(db)
+            for dst, src in zip(outs_h, (o.permute(0, 2, 1, 3), dq.permute(0, 2, 1, 3), dk.permute(0, 2, 1, 3),
+                                         dv.permute(0, 2, 1, 3), db)):
+                dst.copy_(src, non_blocking=True)
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(e2e_steps):
+            e2e_step()
+        e1.record()
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        dev_ms = e0.elapsed_time(e1)
+        tt = torch.tensor([max(wall, dev_ms)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tt.item()) / e2e_steps
+        e2e = {"value": world * F_step / (e2e_ms * 1e-3) / 1e12, "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps,
+               "api": "flasht5_b200.flash_attention_v2_bias + torch.autograd.grad (pinned host q,k,v,bias,dO in; "
+                      "o,dq,dk,dv,dbias out to pinned host)"}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only; bounded sample) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        tf, sec, cores, sample = cpu_eager_attention(sample_b=8, iters=5, warmup=1)
+        cpu = {"value": tf, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "sec_per_iter": sec}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": WB * world, "seq_len": WS, "parallelism": "dp%d" % world,
+                       "l2": "inputs rotate over %d buffer sets of 185 MB each (> 126 MB L2)" % NSETS,
+                       "exchange": "fp32 NCCL all-reduce of dBias per step" if world > 1 else "none"},
+            "tokens_per_s": world * B * S / (ms_step * 1e-3),
+            "frac_of_peak": value / (world * peak), "peak_tflops_per_gpu": peak, "peak_source": peak_src,
+            "gpu_launches": int(launches), "launches_per_step": launches / args.steps,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -59,6 +59,8 @@ SYMBOLS = {
     "b200t5_last_error": (C.c_char_p, []),
     "b200t5_launch_count": (C.c_uint64, []),
     "b200t5_device_supported": (_i32, [_i32]),
+    "b200t5_profile_enable": (_i32, [_i32]),
+    "b200t5_profile_collect": (_i32, [C.POINTER(C.c_int), C.POINTER(C.c_float), _i32]),
 }
 ABI_VERSION = 1
 
@@ -123,3 +125,16 @@ def stream_ptr(device: torch.device) -> int:
 
 def strides4(t: torch.Tensor):
     return I64x4(*t.stride())
+
+
+def profile_enable(on: bool):
+    load().b200t5_profile_enable(1 if on else 0)
+
+
+def profile_collect(cap: int = 4096):
+    """[(kernel_id, ms), ...] for the main attention kernels launched since the last collect
+    (synchronise the stream first)."""
+    ids = (C.c_int * cap)()
+    ms = (C.c_float * cap)()
+    n = load().b200t5_profile_collect(ids, ms, cap)
+    return [(int(ids[i]), float(ms[i])) for i in range(n)]

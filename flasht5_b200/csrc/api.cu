@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "../../include/b200t5.h"
 #include "common.cuh"
@@ -31,6 +32,40 @@ static int fail(int code, const char* fmt, ...) {
 static int fail_cuda(cudaError_t e, const char* what) {
     return fail(B200T5_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
 }
+
+// ------------------------------------------------------------------------------------------
+// optional per-kernel event timing (b200t5_profile_*)
+// ------------------------------------------------------------------------------------------
+struct ProfRecord {
+    int id;
+    cudaEvent_t start, stop;
+};
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<ProfRecord> g_prof;
+
+struct ProfScope {
+    bool active = false;
+    ProfRecord rec{};
+    cudaStream_t stream;
+    ProfScope(int id, cudaStream_t s) : stream(s) {
+        if (!g_prof_on) return;
+        if (cudaEventCreate(&rec.start) != cudaSuccess) return;
+        if (cudaEventCreate(&rec.stop) != cudaSuccess) {
+            cudaEventDestroy(rec.start);
+            return;
+        }
+        rec.id = id;
+        active = true;
+        cudaEventRecord(rec.start, stream);
+    }
+    ~ProfScope() {
+        if (!active) return;
+        cudaEventRecord(rec.stop, stream);
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        g_prof.push_back(rec);
+    }
+};
 
 // RAII: make `device` current for the duration of a call
 struct DeviceGuard {
@@ -208,7 +243,11 @@ extern "C" int b200t5_attn_fwd(const b200t5_attn_params* p) {
     kp.bias_b_bcast = p->bias ? (p->bias_B == 1) : 1;
     kp.bias_h_bcast = p->bias ? (p->bias_H == 1) : 1;
     kp.sm_scale = p->sm_scale;
-    cudaError_t e = launch_attn_fwd(kp, p->D, p->dtype == B200T5_BF16, mode, p->causal != 0, static_cast<cudaStream_t>(p->stream));
+    cudaError_t e;
+    {
+        ProfScope prof(B200T5_KERNEL_ATTN_FWD, static_cast<cudaStream_t>(p->stream));
+        e = launch_attn_fwd(kp, p->D, p->dtype == B200T5_BF16, mode, p->causal != 0, static_cast<cudaStream_t>(p->stream));
+    }
     if (e != cudaSuccess) return fail_cuda(e, "attn_fwd launch");
     return 0;
 }
@@ -295,7 +334,10 @@ extern "C" int b200t5_attn_bwd(const b200t5_attn_params* p) {
     kp.bias_b_bcast = p->bias ? (p->bias_B == 1) : 1;
     kp.bias_h_bcast = p->bias ? (p->bias_H == 1) : 1;
     kp.sm_scale = p->sm_scale;
-    e = launch_attn_bwd(kp, p->D, bf16, mode, p->causal != 0, stream);
+    {
+        ProfScope prof(B200T5_KERNEL_ATTN_BWD, stream);
+        e = launch_attn_bwd(kp, p->D, bf16, mode, p->causal != 0, stream);
+    }
     if (e != cudaSuccess) return fail_cuda(e, "attn_bwd launch");
 
     e = launch_attn_bwd_dq_convert(dq_acc, p->dq, p->dq_strides, p->B, p->H, p->M, p->D, p->sm_scale, bf16, stream);
@@ -396,6 +438,39 @@ extern "C" int b200t5_ce_bwd(const void* logits, const int64_t* labels, const fl
 extern "C" int b200t5_abi_version(void) { return B200T5_ABI_VERSION; }
 extern "C" const char* b200t5_last_error(void) { return g_err; }
 extern "C" uint64_t b200t5_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+extern "C" int b200t5_profile_enable(int enable) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_on = enable != 0;
+    if (!g_prof_on) {
+        for (auto& r : g_prof) {
+            cudaEventDestroy(r.start);
+            cudaEventDestroy(r.stop);
+        }
+        g_prof.clear();
+    }
+    return 0;
+}
+extern "C" int b200t5_profile_collect(int* kernel_ids, float* ms, int cap) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    int n = 0;
+    for (auto& r : g_prof) {
+        float t = -1.f;
+        cudaError_t e = cudaEventElapsedTime(&t, r.start, r.stop);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            t = -1.f;                       // caller did not synchronise
+        }
+        if (n < cap && kernel_ids && ms) {
+            kernel_ids[n] = r.id;
+            ms[n] = t;
+            ++n;
+        }
+        cudaEventDestroy(r.start);
+        cudaEventDestroy(r.stop);
+    }
+    g_prof.clear();
+    return n;
+}
 extern "C" int b200t5_device_supported(int device) {
     int mj = 0;
     int rc = device_cc(device, &mj);

@@ -101,23 +101,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t addr, uint32_t parity) {
     return done != 0;
 }
 
-static __device__ __noinline__ void mbar_wait_slow(uint32_t addr, uint32_t parity) {
-    const uint64_t t0 = globaltimer_ns();
-    uint32_t spins = 0;
-    while (!mbar_try_wait(addr, parity)) {
-        if (B200T5_WATCHDOG_NS != 0 && (++spins & 0xFFu) == 0 && globaltimer_ns() - t0 > B200T5_WATCHDOG_NS) {
-            printf("b200t5: mbarrier deadlock block(%d,%d,%d) thread %d bar@%u parity %u\n", blockIdx.x, blockIdx.y,
-                   blockIdx.z, threadIdx.x, addr, parity);
-            __trap();
-        }
-    }
-}
-
+// Fully inlined (a real call here would force every live register of the caller -- e.g. a whole row of
+// scores -- to be spilled around it).  The watchdog only reads the timer every 1024 failed probes.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     if (mbar_try_wait(addr, parity)) return;
-    if (mbar_try_wait(addr, parity)) return;
-    mbar_wait_slow(addr, parity);
+    uint32_t spins = 0;
+    uint64_t t0 = 0;
+    while (!mbar_try_wait(addr, parity)) {
+        if (B200T5_WATCHDOG_NS != 0 && (++spins & 0x3FFu) == 0) {
+            const uint64_t now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > B200T5_WATCHDOG_NS) {
+#ifdef B200T5_DEBUG_DEADLOCK
+                printf("b200t5: mbarrier deadlock block(%d,%d,%d) thread %d bar@%u parity %u\n", blockIdx.x, blockIdx.y,
+                       blockIdx.z, threadIdx.x, addr, parity);
+#endif
+                __trap();
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -1,0 +1,36 @@
+"""Data-parallel host logic for the attention operator.
+
+The operator is embarrassingly parallel over batch: rank r of G owns a contiguous slice of the
+batch and runs the kernels on it with no communication.  The single exchange is in the backward
+and only because `bias` is one shared (1, H, M, N) tensor: dBias = sum over ranks of the local
+dBias.  That is a plain all-reduce (NCCL over NVLink on the GPU box, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+__all__ = ["shard_batch", "allreduce_dbias"]
+
+
+def shard_batch(global_batch: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """[start, stop) of the batch rows rank `rank` owns; the first `global_batch % world_size` ranks
+    get one extra row (same rule as torch.tensor_split)."""
+    if world_size < 1 or not (0 <= rank < world_size):
+        raise ValueError(f"bad rank/world_size {rank}/{world_size}")
+    base, extra = divmod(global_batch, world_size)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def allreduce_dbias(dbias: Optional[torch.Tensor], group=None) -> Optional[torch.Tensor]:
+    """Sum a batch-broadcast dBias over the data-parallel group.  The sum is done in fp32 (each rank's
+    dBias is already a rounded 16-bit tensor; summing G of them in 16 bits would add G roundings) and
+    cast back once.  No-op without an initialised process group or with a single rank."""
+    if dbias is None or not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return dbias
+    acc = dbias.float()
+    dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
+    return acc.to(dbias.dtype)

@@ -133,6 +133,18 @@ B200T5_API uint64_t b200t5_launch_count(void);           /* kernels launched by 
 /* 1 if `device` is an sm_100 part this library can run on, 0 otherwise, negative on CUDA error */
 B200T5_API int b200t5_device_supported(int device);
 
+/* ------------------------------------------------------------------------------------------------
+ * Per-kernel device timing (measurement hook for bench.py's roofline leg; off by default).
+ * While enabled, the two main attention kernels are bracketed with CUDA events recorded on the launch
+ * stream.  b200t5_profile_collect() must be called after the caller has synchronised that stream; it
+ * writes up to `cap` (kernel id, milliseconds) pairs in launch order, returns how many, and clears
+ * the list.  Kernel ids: 1 = attention forward, 2 = attention backward (the fused dQ/dK/dV/dS kernel).
+ * Not thread-safe against concurrent launches; not for use under CUDA-graph capture.
+ * ---------------------------------------------------------------------------------------------- */
+enum { B200T5_KERNEL_ATTN_FWD = 1, B200T5_KERNEL_ATTN_BWD = 2 };
+B200T5_API int b200t5_profile_enable(int enable);
+B200T5_API int b200t5_profile_collect(int* kernel_ids, float* ms, int cap);
+
 #ifdef __cplusplus
 }
 #endif

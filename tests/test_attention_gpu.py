@@ -1,0 +1,313 @@
+"""GPU parity tests of the attention operator, through the public op (which calls the C ABI).
+
+Bars (stated here once):
+  * vs the REFERENCE golden vectors (tests/golden/attn_*.npz, produced by the reference's own attn_ref +
+    autograd in fp32) and vs the fp64 oracle on seeded inputs: relative Frobenius error
+        bf16:  O, dV <= 4e-3;  dQ, dK, dBias <= 1.2e-2        fp16:  O, dV <= 6e-4;  dQ, dK, dBias <= 2e-3
+    (16-bit outputs: merely rounding the exact answer gives 1.6e-3 in bf16 / 2e-4 in fp16 -- SURVEY.md
+    section 4; dS is rounded to 16 bits before the dQ/dK contractions exactly as the reference does);
+    LSE (fp32) <= 1e-5 max abs relative to |L|.
+  * the reference's own rule (tests/fa2_triton/test_fa2_bias.py:28,64-67):
+        max|new - fp32| <= 2 * max|eager_lowp - fp32| + 1e-5
+  * at BASELINE.json's full size: size-independent properties (row-stochasticity, causality,
+    batch equivariance, dBias additivity over the batch, linearity in dO).
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import attn_bias_ref as orc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+TOL = {torch.bfloat16: {"o": 4e-3, "dv": 4e-3, "dq": 1.2e-2, "dk": 1.2e-2, "dbias": 1.2e-2},
+       torch.float16: {"o": 6e-4, "dv": 6e-4, "dq": 2e-3, "dk": 2e-3, "dbias": 2e-3}}
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def _run(q, k, v, bias, do, causal, scale):
+    from flasht5_b200 import flash_attention_v2_bias
+    qd, kd, vd = (t.to(DEV).requires_grad_(True) for t in (q, k, v))
+    bd = bias.to(DEV).requires_grad_(True) if bias is not None else None
+    o = flash_attention_v2_bias(qd, kd, vd, bd, causal, scale)
+    ins = (qd, kd, vd) + ((bd,) if bd is not None else ())
+    grads = torch.autograd.grad(o, ins, do.to(DEV))
+    torch.cuda.synchronize()
+    out = {"o": o, "dq": grads[0], "dk": grads[1], "dv": grads[2]}
+    if bd is not None:
+        out["dbias"] = grads[3]
+    return out
+
+
+def test_cuda_library_is_loaded_and_launches():
+    from flasht5_b200 import _cabi
+    lib = _cabi.load()
+    assert lib.b200t5_device_supported(0) == 1, _cabi.last_error()
+    n0 = _cabi.launch_count()
+    q = torch.randn(1, 1, 128, 64, device=DEV, dtype=torch.bfloat16)
+    torch.ops.b200t5.attn_bias_fwd(q, q, q, None, False, 1.0)
+    torch.cuda.synchronize()
+    assert _cabi.launch_count() == n0 + 1
+    with open("/proc/self/maps") as f:
+        assert "libb200t5.so" in f.read()
+
+
+ATTN_FILES = sorted(glob.glob(os.path.join(GOLDEN, "attn_*.npz")))
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("path", ATTN_FILES, ids=[os.path.basename(p)[:-4] for p in ATTN_FILES])
+def test_against_reference_golden(path, dtype):
+    """Inputs in the fixtures are bf16-exact; fp16 inputs are re-rounded, so fp16 is compared with the oracle."""
+    z = np.load(path)
+    q, k, v, do = (_t(z[n]).to(dtype) for n in ("q", "k", "v", "do"))
+    bias = _t(z["bias"]).to(dtype) if "bias" in z.files else None
+    causal = bool(z["causal"])
+    scale = None if np.isnan(z["sm_scale"]) else float(z["sm_scale"])
+    valid = _t(z["valid_rows"])
+    do = torch.where(valid.view(1, 1, -1, 1), do, torch.zeros_like(do))
+    got = _run(q, k, v, bias, do, causal, scale)
+    if dtype == torch.bfloat16:
+        ref = {n: _t(z[n]) for n in ("o", "dq", "dk", "dv")}
+        if bias is not None:
+            ref["dbias"] = _t(z["dbias"])
+    else:
+        o, L, dq, dk, dv, db = orc.attn_fwd_bwd(q.float(), k.float(), v.float(), None if bias is None else bias.float(),
+                                                 do.float(), causal, scale)
+        ref = {"o": o, "dq": dq, "dk": dk, "dv": dv}
+        if bias is not None:
+            ref["dbias"] = db
+    for name, r in ref.items():
+        mx, rf = orc.error_metrics(got[name], r)
+        assert rf <= TOL[dtype][name], (name, mx, rf)
+        assert got[name].dtype == dtype and got[name].shape == r.shape
+    # rows with no visible key: O = 0 exactly (reference :470-473)
+    assert torch.all(got["o"][:, :, ~valid.to(DEV)] == 0)
+
+
+# B, H, M, N, D, dtype, bias kind, causal, scale, layout
+CASES = [
+    (1, 1, 128, 128, 64, torch.bfloat16, None, False, 0.125, "bhsd"),
+    (2, 2, 128, 128, 64, torch.bfloat16, "1H", False, 1.0, "bhsd"),
+    (2, 2, 256, 256, 64, torch.bfloat16, "1H", True, 1.0, "bshd"),
+    (2, 3, 200, 328, 64, torch.bfloat16, "1H", False, 1.0, "bshd"),
+    (2, 2, 256, 256, 64, torch.float16, "1H", False, 1.0, "bshd"),
+    (1, 2, 256, 256, 128, torch.bfloat16, "1H", False, 1.0, "bshd"),
+    (2, 2, 512, 512, 128, torch.bfloat16, "1H", True, 1.0, "bshd"),
+    (1, 2, 256, 256, 32, torch.bfloat16, "1H", False, 1.0, "bshd"),
+    (1, 2, 256, 256, 16, torch.bfloat16, "1H", False, 1.0, "bshd"),
+    (2, 2, 300, 333, 32, torch.float16, "1H", True, 0.5, "bshd"),
+    (2, 2, 300, 333, 16, torch.bfloat16, "B1", True, 0.5, "bshd"),
+    (2, 2, 130, 131, 64, torch.bfloat16, "1H", True, 1.0, "bshd"),        # unaligned bias rows -> pointer path
+    (2, 2, 256, 256, 64, torch.bfloat16, "BH", True, 1.0, "bshd"),
+    (2, 2, 256, 256, 64, torch.bfloat16, "11", False, 1.0, "bshd"),        # head-broadcast: the reference races here
+    (1, 2, 384, 200, 64, torch.bfloat16, "1H", True, 1.0, "bshd"),         # M > N causal: empty rows
+    (2, 4, 512, 384, 64, torch.bfloat16, None, False, 1.0, "bshd"),        # cross attention
+    (1, 1, 1, 1, 64, torch.bfloat16, "1H", False, 1.0, "bhsd"),            # smallest problem
+    (1, 2, 7, 1000, 64, torch.float16, "1H", False, 1.0, "bhsd"),          # few queries, many keys
+    (1, 2, 1000, 5, 64, torch.bfloat16, "1H", False, 1.0, "bhsd"),
+    (2, 4, 512, 612, 128, torch.float16, "BH", True, 1.0, "bhsd"),         # reference test shape (test_fa2_bias.py:9-12)
+    (2, 4, 1024, 1045, 64, torch.bfloat16, "11", False, 1.0, "bhsd"),      # reference test shape, bwd bias (1,1,M,N)
+]
+
+
+def _make(B, H, M, N, D, dtype, bk, layout, seed):
+    g = torch.Generator().manual_seed(seed)
+
+    def mk(s):
+        if layout == "bshd":
+            return torch.randn(B, s, H, D, generator=g).to(dtype).permute(0, 2, 1, 3)
+        return torch.randn(B, H, s, D, generator=g).to(dtype)
+    q, k, v, do = mk(M), mk(N), mk(N), mk(M)
+    bias = None
+    if bk is not None:
+        shape = {"1H": (1, H, M, N), "BH": (B, H, M, N), "11": (1, 1, M, N), "B1": (B, 1, M, N)}[bk]
+        bias = torch.randn(*shape, generator=g).to(dtype)
+    return q, k, v, bias, do
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "B%dH%dM%dN%dD%d_%s_%s_%s" % (c[0], c[1], c[2], c[3], c[4], str(c[5])[6:], c[6], "c" if c[7] else "nc"))
+def test_against_oracle_seeded(case):
+    B, H, M, N, D, dtype, bk, causal, scale, layout = case
+    q, k, v, bias, do = _make(B, H, M, N, D, dtype, bk, layout, seed=B * 1000 + M + N + D)
+    o, L, dq, dk, dv, db = orc.attn_fwd_bwd(q.float(), k.float(), v.float(), None if bias is None else bias.float(),
+                                             do.float(), causal, scale)
+    got = _run(q, k, v, bias, do, causal, scale)
+    ref = {"o": o, "dq": dq, "dk": dk, "dv": dv}
+    if bias is not None:
+        ref["dbias"] = db
+    for name, r in ref.items():
+        mx, rf = orc.error_metrics(got[name], r)
+        assert rf <= TOL[dtype][name], (name, mx, rf)
+    # output keeps q's strides (reference :58, empty_like) so the model's permute+reshape stays free
+    assert got["o"].stride() == q.stride() or not q.is_contiguous()
+    # LSE through the raw op
+    _, Lg = torch.ops.b200t5.attn_bias_fwd(q.to(DEV), k.to(DEV), v.to(DEV), None if bias is None else bias.to(DEV), causal, float(scale))
+    fin = torch.isfinite(L)
+    assert torch.equal(torch.isfinite(Lg).cpu(), fin)
+    assert torch.allclose(Lg.cpu().double()[fin], L[fin], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_reference_tolerance_rule(causal, dtype):
+    """tests/fa2_triton/test_fa2_bias.py:16-67 with its shapes: err_new <= 2 * err_eager_lowp + 1e-5 (max abs)."""
+    for (B, H, M, N, D) in ((2, 4, 512, 612, 128), (2, 4, 1024, 1045, 64)):
+        g = torch.Generator().manual_seed(M + N)
+        q = torch.randn(B, H, M, D, generator=g).to(dtype)
+        k = torch.randn(B, H, N, D, generator=g).to(dtype)
+        v = torch.randn(B, H, N, D, generator=g).to(dtype)
+        bias = torch.randn(1, H, M, N, generator=g).to(dtype)
+        do = torch.randn(B, H, M, D, generator=g).to(dtype)
+        o64, L, dq64, dk64, dv64, db64 = orc.attn_fwd_bwd(q.float(), k.float(), v.float(), bias.float(), do.float(), causal, 1.0)
+        # eager low-precision yardstick on the GPU (same maths as attn_ref(upcast=False))
+        ql, kl, vl, bl = (t.to(DEV).requires_grad_(True) for t in (q, k, v, bias))
+        o_low = orc.attn_eager_lowp(ql, kl, vl, bl, causal, 1.0)
+        g_low = torch.autograd.grad(o_low, (ql, kl, vl, bl), do.to(DEV))
+        got = _run(q, k, v, bias, do, causal, 1.0)
+        for name, ref64, low in (("o", o64, o_low), ("dq", dq64, g_low[0]), ("dk", dk64, g_low[1]),
+                                 ("dv", dv64, g_low[2]), ("dbias", db64, g_low[3])):
+            err_new = (got[name].double().cpu() - ref64).abs().max().item()
+            err_low = (low.detach().double().cpu() - ref64).abs().max().item()
+            assert err_new <= 2 * err_low + 1e-5, (name, (B, H, M, N, D), err_new, err_low)
+
+
+def test_t5_structured_bias_all_bucket_kinds():
+    H, M, N = 4, 384, 384
+    g = torch.Generator().manual_seed(77)
+    table = 0.5 * torch.randn(32, H, generator=g)
+    for causal in (False, True):
+        bias = orc.t5_bias(table, M, N, bidirectional=not causal).to(torch.bfloat16)
+        q, k, v, _, do = _make(2, H, M, N, 64, torch.bfloat16, None, "bshd", 5)
+        o, L, dq, dk, dv, db = orc.attn_fwd_bwd(q.float(), k.float(), v.float(), bias.float(), do.float(), causal, 1.0)
+        got = _run(q, k, v, bias, do, causal, 1.0)
+        for name, r in (("o", o), ("dq", dq), ("dk", dk), ("dv", dv), ("dbias", db)):
+            mx, rf = orc.error_metrics(got[name], r)
+            assert rf <= TOL[torch.bfloat16][name], (causal, name, mx, rf)
+
+
+def test_masking_folded_into_bias_finfo_min():
+    """use_masking path of the model (modeling_flash_t5.py:266-270): padding keys get finfo.min in a full-size bias."""
+    B, H, M, N, D = 2, 2, 256, 256, 64
+    q, k, v, bias, do = _make(B, H, M, N, D, torch.bfloat16, "BH", "bshd", 11)
+    bias[1, :, :, 200:] = torch.finfo(torch.bfloat16).min
+    o, L, dq, dk, dv, db = orc.attn_fwd_bwd(q.float(), k.float(), v.float(), bias.float(), do.float(), False, 1.0)
+    got = _run(q, k, v, bias, do, False, 1.0)
+    for name, r in (("o", o), ("dq", dq), ("dk", dk), ("dv", dv), ("dbias", db)):
+        mx, rf = orc.error_metrics(got[name], r)
+        assert rf <= TOL[torch.bfloat16][name], (name, mx, rf)
+    assert torch.all(got["dk"][1, :, 200:] == 0) and torch.all(got["dv"][1, :, 200:] == 0)
+
+
+def test_error_behaviour_matches_reference():
+    from flasht5_b200 import flash_attention_v2_bias
+    q = torch.randn(1, 2, 64, 48, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(AssertionError):                         # reference :233-234
+        flash_attention_v2_bias(q, q, q, None)
+    q = torch.randn(1, 2, 64, 64, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises((ValueError, RuntimeError)):
+        flash_attention_v2_bias(q, q, q, torch.zeros(3, 2, 64, 64, device=DEV, dtype=torch.bfloat16))
+    with pytest.raises((TypeError, RuntimeError)):
+        flash_attention_v2_bias(q.float(), q.float(), q.float(), None)
+
+
+def test_cuda_graph_capture_and_replay():
+    """The C ABI never allocates or synchronises, so the ops are graph-capturable."""
+    B, H, S, D = 2, 4, 256, 64
+    q, k, v, bias, do = (t.to(DEV) if t is not None else None for t in _make(B, H, S, S, D, torch.bfloat16, "1H", "bshd", 3))
+    o_ref, L_ref = torch.ops.b200t5.attn_bias_fwd(q, k, v, bias, True, 1.0)
+    g_ref = torch.ops.b200t5.attn_bias_bwd(o_ref, do, q, k, v, bias, L_ref, True, 1.0)
+    torch.cuda.synchronize()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        torch.ops.b200t5.attn_bias_fwd(q, k, v, bias, True, 1.0)
+    torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        o, L = torch.ops.b200t5.attn_bias_fwd(q, k, v, bias, True, 1.0)
+        grads = torch.ops.b200t5.attn_bias_bwd(o, do, q, k, v, bias, L, True, 1.0)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(o, o_ref) and torch.equal(L, L_ref)
+    for a, b_ in zip(grads[1:3], g_ref[1:3]):                   # dK, dV are deterministic
+        assert torch.equal(a, b_)
+    for a, b_ in ((grads[0], g_ref[0]), (grads[3], g_ref[3])):  # dQ: fp32 reduce-add order may differ
+        assert torch.allclose(a.float(), b_.float(), atol=2e-2, rtol=2e-2)
+
+
+# ---------------------------------------------------------------------------------------------
+# full BASELINE.json size: properties instead of an oracle that would take minutes on the CPU
+# ---------------------------------------------------------------------------------------------
+def _full(seed=0, B=32, H=8, S=1024, D=64, causal=False):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    mk = lambda: torch.randn(B, S, H, D, generator=g, device=DEV).to(torch.bfloat16).permute(0, 2, 1, 3)  # noqa: E731
+    q, k, v, do = mk(), mk(), mk(), mk()
+    bias = (0.5 * torch.randn(1, H, S, S, generator=g, device=DEV)).to(torch.bfloat16)
+    return q, k, v, bias, do
+
+
+def test_full_size_row_stochastic_and_matches_fp32_torch():
+    """Headline shape (32,8,1024,1024,64): V = 1 gives O = 1; and one (b,h) slice is checked against fp32 torch
+    on the GPU (a floating-point kernel may keep a torch fp32 reference: task text, section 3)."""
+    q, k, v, bias, do = _full(1)
+    o1, _ = torch.ops.b200t5.attn_bias_fwd(q, k, torch.ones_like(v), bias, False, 1.0)
+    assert torch.all((o1.float() - 1).abs() <= 2 ** -7)
+    o, L = torch.ops.b200t5.attn_bias_fwd(q, k, v, bias, False, 1.0)
+    for (b, h) in ((0, 0), (31, 7), (13, 3)):
+        s = q[b, h].float() @ k[b, h].float().T + bias[0, h].float()
+        assert torch.allclose(L[b, h], torch.logsumexp(s, -1), atol=1e-4, rtol=1e-5)
+        ref = torch.softmax(s, -1) @ v[b, h].float()
+        mx, rf = orc.error_metrics(o[b, h], ref)
+        assert rf < 4e-3, (b, h, mx, rf)
+
+
+def test_full_size_backward_properties():
+    q, k, v, bias, do = _full(2)
+    o, L = torch.ops.b200t5.attn_bias_fwd(q, k, v, bias, False, 1.0)
+    dq, dk, dv, db = torch.ops.b200t5.attn_bias_bwd(o, do, q, k, v, bias, L, False, 1.0)
+    # (1) batch equivariance: batch row 5 alone gives the same dQ/dK/dV rows
+    sl = slice(5, 6)
+    o5, L5 = torch.ops.b200t5.attn_bias_fwd(q[sl], k[sl], v[sl], bias, False, 1.0)
+    dq5, dk5, dv5, db5 = torch.ops.b200t5.attn_bias_bwd(o5, do[sl], q[sl], k[sl], v[sl], bias, L5, False, 1.0)
+    assert torch.equal(o5, o[sl]) and torch.equal(L5, L[sl])
+    assert torch.equal(dk5, dk[sl]) and torch.equal(dv5, dv[sl])
+    assert torch.allclose(dq5.float(), dq[sl].float(), atol=3e-2, rtol=2e-2)
+    # (2) dBias additivity: sum of per-half-batch dBias == full-batch dBias (up to 16-bit rounding)
+    halves = []
+    for s0 in (slice(0, 16), slice(16, 32)):
+        oh, Lh = torch.ops.b200t5.attn_bias_fwd(q[s0], k[s0], v[s0], bias, False, 1.0)
+        halves.append(torch.ops.b200t5.attn_bias_bwd(oh, do[s0], q[s0], k[s0], v[s0], bias, Lh, False, 1.0)[3].float())
+    mx, rf = orc.error_metrics(halves[0] + halves[1], db.float())
+    assert rf < 6e-3, (mx, rf)
+    # (3) each row of dS sums to ~0 (softmax Jacobian): sum_n dBias[h,m,n] ~ 0 relative to its L1 mass
+    rel = db.float().sum(-1).abs() / db.float().abs().sum(-1).clamp_min(1e-6)
+    assert rel.max() < 2e-2
+    # (4) one (b,h) slice against fp32 torch autograd on the GPU
+    b, h = 3, 6
+    qq, kk, vv = (t[b, h].float().requires_grad_(True) for t in (q, k, v))
+    out = torch.softmax(qq @ kk.T + bias[0, h].float(), -1) @ vv
+    gq, gk, gv = torch.autograd.grad(out, (qq, kk, vv), do[b, h].float())
+    for name, mine, r in (("dq", dq[b, h], gq), ("dk", dk[b, h], gk), ("dv", dv[b, h], gv)):
+        mx, rf = orc.error_metrics(mine, r)
+        assert rf <= TOL[torch.bfloat16][name], (name, mx, rf)
+
+
+def test_full_size_causality():
+    """Causal: changing keys/values at positions > m never changes row m (S=1024 headline shape, B=8)."""
+    q, k, v, bias, do = _full(3, B=8)
+    o, L = torch.ops.b200t5.attn_bias_fwd(q, k, v, bias, True, 1.0)
+    k2, v2 = k.clone(), v.clone()
+    k2[:, :, 700:] = torch.randn_like(k2[:, :, 700:])
+    v2[:, :, 700:] = torch.randn_like(v2[:, :, 700:])
+    o2, L2 = torch.ops.b200t5.attn_bias_fwd(q, k2, v2, bias, True, 1.0)
+    assert torch.equal(o[:, :, :700], o2[:, :, :700]) and torch.equal(L[:, :, :700], L2[:, :, :700])
+    assert not torch.equal(o[:, :, 700:], o2[:, :, 700:])
