@@ -12,7 +12,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200t5.so")
+LIB_PATH = os.environ.get("B200T5_LIB") or os.path.join(_HERE, "libb200t5.so")   # env override: developer builds only
 
 F16, BF16, F32 = 0, 1, 2
 _DTYPE_CODE = {torch.float16: F16, torch.bfloat16: BF16, torch.float32: F32}

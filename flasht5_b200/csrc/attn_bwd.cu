@@ -394,11 +394,13 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdKernelParams p) {
                     *reinterpret_cast<uint4*>(sDS + off) = make_uint4(dd[c8 * 4], dd[c8 * 4 + 1], dd[c8 * 4 + 2], dd[c8 * 4 + 3]);
                 }
             }
+            // one proxy fence covers both hazards: the generic reads of the bias tile must complete before
+            // TMA overwrites it (WAR), and the generic writes of P / dS must be visible to UMMA / TMA (RAW)
+            fence_proxy_async_smem();
             if (kBiasMode == 1) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(b_empty + wg);
             }
-            fence_proxy_async_smem();
             named_bar_sync(1, 256);
             if (ctid == 0) {
                 mbar_arrive(pds_full);

@@ -12,6 +12,8 @@
 //                      rescale of O in TMEM), P -> TMEM as packed 16-bit, epilogue O / l and LSE
 //
 // TMEM columns: S [0,128) fp32 | O [128,128+D) fp32 | P [128+D, 128+D+64) packed 16-bit pairs.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -287,6 +289,10 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdKernelParams p) {
                             x[c + 1] = fmaf(x[c + 1], p.sm_scale, f.y);
                         }
                     }
+                    // WAR across proxies: these generic-proxy reads must have completed before the TMA
+                    // (async proxy) may overwrite the stage.  Without the fence ~0.1% of rows picked up
+                    // bytes of the NEXT tile when two CTAs shared an SM (measured on B200).
+                    fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bars.b_empty + s);
                 }
@@ -436,6 +442,14 @@ static cudaError_t launch_fwd_inst(const AttnFwdKernelParams& kp, cudaStream_t s
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     if (e != cudaSuccess) return e;
     const int grid = kp.B * kp.H * kp.num_m_blocks;
+    static const int extra_smem = getenv("B200T5_DEBUG_EXTRA_SMEM") ? atoi(getenv("B200T5_DEBUG_EXTRA_SMEM")) : 0;
+    if (extra_smem > 0) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal + extra_smem);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, 256, L::kTotal + extra_smem, stream>>>(kp);
+        count_launch();
+        return cudaGetLastError();
+    }
     kern<<<grid, 256, L::kTotal, stream>>>(kp);
     count_launch();
     return cudaGetLastError();
