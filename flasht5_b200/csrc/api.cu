@@ -254,8 +254,8 @@ extern "C" int b200t5_attn_fwd(const b200t5_attn_params* p) {
 
 namespace {
 struct BwdWorkspace {
-    size_t delta_off, dq_off, ds_off, total;
-    int n_pad;
+    size_t delta_off, dq_off, ds_off, ds_bytes, total;
+    int n_pad, ds_groups, ds_use_reduce;
 };
 BwdWorkspace bwd_workspace_layout(const b200t5_attn_params* p) {
     BwdWorkspace w;
@@ -265,7 +265,26 @@ BwdWorkspace bwd_workspace_layout(const b200t5_attn_params* p) {
     w.delta_off = 0;
     w.dq_off = align(rows * sizeof(float));
     w.ds_off = w.dq_off + align(rows * p->D * sizeof(float));
-    w.total = w.ds_off + (p->bias ? align(rows * (size_t)w.n_pad * 2) : 0);
+    // dS surface: per-batch bias -> one slice per batch (plain stores); batch-broadcast bias -> the batch is
+    // folded into ds_groups slices of <= 8 (<= B/16 for huge B) batches each by TMA reduce-add in the bias dtype,
+    // and the slices are summed in fp32 afterwards.  Keeps the surface L2-sized (67 MB at the headline shape
+    // instead of 537 MB) while bounding the 16-bit accumulation depth.
+    w.ds_groups = 0;
+    w.ds_use_reduce = 0;
+    size_t ds_bytes = 0;
+    if (p->bias) {
+        if (p->bias_B == 1 && p->B > 1) {
+            int g = (p->B + 7) / 8;
+            if (g > 16) g = 16;
+            w.ds_groups = g;
+            w.ds_use_reduce = 1;
+        } else {
+            w.ds_groups = p->B;
+        }
+        ds_bytes = (size_t)w.ds_groups * p->H * p->M * (size_t)w.n_pad * 2;
+    }
+    w.ds_bytes = ds_bytes;
+    w.total = w.ds_off + align(ds_bytes);
     return w;
 }
 }  // namespace
@@ -322,8 +341,14 @@ extern "C" int b200t5_attn_bwd(const b200t5_attn_params* p) {
     }
     if (mode != 0) {
         // dS tiles always go to the (B, H, M, n_pad) 16-bit workspace through TMA stores
-        if ((rc = make_map_4d(&kp.map_ds, ds_ws, 2, dt, p->N, p->M, p->H, p->B, w.n_pad, (int64_t)p->M * w.n_pad, (int64_t)p->H * p->M * w.n_pad, 64, 128, "dS workspace"))) return rc;
+        if ((rc = make_map_4d(&kp.map_ds, ds_ws, 2, dt, p->N, p->M, p->H, w.ds_groups, w.n_pad, (int64_t)p->M * w.n_pad, (int64_t)p->H * p->M * w.n_pad, 64, 128, "dS workspace"))) return rc;
+        if (w.ds_use_reduce) {
+            e = cudaMemsetAsync(ds_ws, 0, w.ds_bytes, stream);
+            if (e != cudaSuccess) return fail_cuda(e, "dS workspace memset");
+        }
     }
+    kp.ds_groups = w.ds_groups > 0 ? w.ds_groups : 1;
+    kp.ds_use_reduce = w.ds_use_reduce;
     kp.dk = p->dk; kp.dk_sb = p->dk_strides[0]; kp.dk_sh = p->dk_strides[1]; kp.dk_sn = p->dk_strides[2];
     kp.dv = p->dv; kp.dv_sb = p->dv_strides[0]; kp.dv_sh = p->dv_strides[1]; kp.dv_sn = p->dv_strides[2];
     kp.lse = p->lse;
@@ -344,7 +369,8 @@ extern "C" int b200t5_attn_bwd(const b200t5_attn_params* p) {
     if (e != cudaSuccess) return fail_cuda(e, "attn_bwd_dq_convert launch");
 
     if (mode != 0) {
-        e = launch_dbias_reduce(ds_ws, w.n_pad, p->dbias, p->dbias_strides, p->B, p->H, p->M, p->N, p->bias_B == 1, p->bias_H == 1, p->causal != 0, bf16, stream);
+        // the reduce kernel sees the group dim as its "batch": (groups, H, M, n_pad) -> dbias
+        e = launch_dbias_reduce(ds_ws, w.n_pad, p->dbias, p->dbias_strides, w.ds_groups, p->H, p->M, p->N, p->bias_B == 1, p->bias_H == 1, p->causal != 0, bf16, stream);
         if (e != cudaSuccess) return fail_cuda(e, "dbias_reduce launch");
     }
     return 0;

@@ -20,6 +20,7 @@
 // TMEM columns: S [0,128) | dP [128,256) | dV [256,256+D) | dK [256+D,256+2D) | dQ [256+2D, 256+3D)
 // (D = 128: dQ aliases the S columns).
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -405,8 +406,14 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdKernelParams p) {
             if (ctid == 0) {
                 mbar_arrive(pds_full);
                 if (kBiasMode != 0) {
-                    tma_store_4d(&p.map_ds, smem + C::kDS, col0, mrow0, h, b);
-                    tma_store_4d(&p.map_ds, smem + C::kDS + kHalfBytes, col0 + 64, mrow0, h, b);
+                    const int g = b % p.ds_groups;
+                    if (p.ds_use_reduce) {
+                        tma_reduce_add_4d(&p.map_ds, smem + C::kDS, col0, mrow0, h, g);
+                        tma_reduce_add_4d(&p.map_ds, smem + C::kDS + kHalfBytes, col0 + 64, mrow0, h, g);
+                    } else {
+                        tma_store_4d(&p.map_ds, smem + C::kDS, col0, mrow0, h, g);
+                        tma_store_4d(&p.map_ds, smem + C::kDS + kHalfBytes, col0 + 64, mrow0, h, g);
+                    }
                     bulk_commit_group();
                     if (C::kDqAliasesDs) bulk_wait_group_read<0>();
                 }
@@ -674,6 +681,8 @@ static cudaError_t launch_bwd_d(const AttnBwdKernelParams& kp, int bias_mode, bo
 
 cudaError_t launch_attn_bwd(const AttnBwdKernelParams& kp, int D, bool bf16, int bias_mode, bool causal,
                             cudaStream_t stream) {
+    static const bool force_v1 = getenv("B200T5_DEBUG_BWD_V1") != nullptr;
+    if (D <= 64 && !force_v1) return launch_attn_bwd_v2(kp, D, bf16, bias_mode, causal, stream);
 #define B200T5_BWD_CASE(DD)                                                              \
     case DD:                                                                             \
         return bf16 ? launch_bwd_d<DD, true>(kp, bias_mode, causal, stream)              \

@@ -150,6 +150,16 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
         : "memory");
 }
 
+// shared -> global element-wise ADD through a tensor map (the element type comes from the map); executed at L2
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2,
+                                                  int c3) {
+    asm volatile(
+        "cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+        :
+        : "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
 // smem (contiguous bytes) --add.f32--> global (contiguous bytes), executed by the TMA unit at L2
 __device__ __forceinline__ void bulk_reduce_add_f32(float* gdst, const void* smem_src, uint32_t bytes) {
     asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"

@@ -44,12 +44,17 @@ struct AttnBwdKernelParams {
     int num_m_blocks, num_n_blocks;
     int bias_b_bcast, bias_h_bcast;
     float sm_scale;
+    // dS surface: (N, M, H, ds_groups) 16-bit.  Batch b adds its tile into group b % ds_groups with a TMA
+    // reduce-add (ds_use_reduce = 1, surface pre-zeroed) or owns its slice and stores (ds_use_reduce = 0).
+    int ds_groups, ds_use_reduce;
 };
 
 cudaError_t launch_attn_fwd(const AttnFwdKernelParams& kp, int D, bool bf16, int bias_mode, bool causal,
                             cudaStream_t stream);
 cudaError_t launch_attn_bwd(const AttnBwdKernelParams& kp, int D, bool bf16, int bias_mode, bool causal,
-                            cudaStream_t stream);
+                            cudaStream_t stream);        // dispatches: D <= 64 -> pipelined v2 kernel, D = 128 -> v1
+cudaError_t launch_attn_bwd_v2(const AttnBwdKernelParams& kp, int D, bool bf16, int bias_mode, bool causal,
+                               cudaStream_t stream);
 
 // delta[b,h,m] = sum_d O*dO  (fp32); also zero-fills the fp32 dQ accumulator.
 cudaError_t launch_attn_bwd_preprocess(const void* o, const int64_t* o_strides, const void* dout,
