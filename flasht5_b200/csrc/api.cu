@@ -255,7 +255,7 @@ extern "C" int b200t5_attn_fwd(const b200t5_attn_params* p) {
 namespace {
 struct BwdWorkspace {
     size_t delta_off, dq_off, ds_off, ds_bytes, total;
-    int n_pad, ds_groups, ds_use_reduce;
+    int n_pad, ds_groups, ds_use_reduce, dq_groups;
 };
 BwdWorkspace bwd_workspace_layout(const b200t5_attn_params* p) {
     BwdWorkspace w;
@@ -264,7 +264,12 @@ BwdWorkspace bwd_workspace_layout(const b200t5_attn_params* p) {
     w.n_pad = round_up8(p->N);
     w.delta_off = 0;
     w.dq_off = align(rows * sizeof(float));
-    w.ds_off = w.dq_off + align(rows * p->D * sizeof(float));
+    // dQ group surface: <= 4 key blocks accumulate (16-bit, at L2) into one group; <= 8 groups
+    const int nnb = (p->N + 127) / 128;
+    int gq = (nnb + 3) / 4;
+    if (gq > 8) gq = 8;
+    w.dq_groups = gq;
+    w.ds_off = w.dq_off + align((size_t)gq * rows * p->D * 2);
     // dS surface: per-batch bias -> one slice per batch (plain stores); batch-broadcast bias -> the batch is
     // folded into ds_groups slices of <= 8 (<= B/16 for huge B) batches each by TMA reduce-add in the bias dtype,
     // and the slices are summed in fp32 afterwards.  Keeps the surface L2-sized (67 MB at the headline shape
@@ -313,10 +318,10 @@ extern "C" int b200t5_attn_bwd(const b200t5_attn_params* p) {
     const bool bf16 = p->dtype == B200T5_BF16;
     uint8_t* ws = static_cast<uint8_t*>(p->workspace);
     float* delta = reinterpret_cast<float*>(ws + w.delta_off);
-    float* dq_acc = reinterpret_cast<float*>(ws + w.dq_off);
+    void* dq_ws = ws + w.dq_off;
     void* ds_ws = ws + w.ds_off;
 
-    cudaError_t e = launch_attn_bwd_preprocess(p->o, p->o_strides, p->dout, p->do_strides, delta, dq_acc, p->B, p->H, p->M, p->D, bf16, stream);
+    cudaError_t e = launch_attn_bwd_preprocess(p->o, p->o_strides, p->dout, p->do_strides, delta, dq_ws, w.dq_groups, p->B, p->H, p->M, p->D, bf16, stream);
     if (e != cudaSuccess) return fail_cuda(e, "attn_bwd_preprocess launch");
 
     const CUtensorMapDataType dt = bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
@@ -327,8 +332,8 @@ extern "C" int b200t5_attn_bwd(const b200t5_attn_params* p) {
     if ((rc = make_map_4d(&kp.map_k, p->k, 2, dt, p->D, p->N, p->H, p->B, p->k_strides[2], p->k_strides[1], p->k_strides[0], boxd, 128, "k"))) return rc;
     if ((rc = make_map_4d(&kp.map_v, p->v, 2, dt, p->D, p->N, p->H, p->B, p->v_strides[2], p->v_strides[1], p->v_strides[0], boxd, 128, "v"))) return rc;
     if ((rc = make_map_4d(&kp.map_do, p->dout, 2, dt, p->D, p->M, p->H, p->B, p->do_strides[2], p->do_strides[1], p->do_strides[0], boxd, 128, "dout"))) return rc;
-    const uint32_t dqbox = p->D >= 32 ? 32 : p->D;
-    if ((rc = make_map_4d(&kp.map_dq, dq_acc, 4, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, p->D, p->M, p->H, p->B, p->D, (int64_t)p->M * p->D, (int64_t)p->H * p->M * p->D, dqbox, 128, "dq accumulator", true))) return rc;
+    if ((rc = make_map_4d(&kp.map_dq, dq_ws, 2, dt, p->D, p->M, p->H, (uint64_t)w.dq_groups * p->B, p->D, (int64_t)p->M * p->D, (int64_t)p->H * p->M * p->D, boxd, 128, "dq group surface", true))) return rc;
+    kp.dq_groups = w.dq_groups;
     const int mode = bias_mode_of(p);
     if (mode == 1) {
         if ((rc = make_map_4d(&kp.map_bias, p->bias, 2, dt, p->N, p->M, p->bias_H, p->bias_B, p->bias_strides[2], p->bias_strides[1], p->bias_strides[0], 64, 128, "bias"))) return rc;
@@ -365,7 +370,7 @@ extern "C" int b200t5_attn_bwd(const b200t5_attn_params* p) {
     }
     if (e != cudaSuccess) return fail_cuda(e, "attn_bwd launch");
 
-    e = launch_attn_bwd_dq_convert(dq_acc, p->dq, p->dq_strides, p->B, p->H, p->M, p->D, p->sm_scale, bf16, stream);
+    e = launch_attn_bwd_dq_convert(dq_ws, w.dq_groups, p->dq, p->dq_strides, p->B, p->H, p->M, p->D, p->sm_scale, bf16, stream);
     if (e != cudaSuccess) return fail_cuda(e, "attn_bwd_dq_convert launch");
 
     if (mode != 0) {

@@ -43,10 +43,10 @@ struct BwdCfg {
     static constexpr uint32_t kSwizzle = kRowBytes == 128 ? kSwz128 : (kRowBytes == 64 ? kSwz64 : kSwz32);
     static constexpr int kQStages = kD <= 64 ? 2 : 1;
     static constexpr bool kLookahead = kQStages == 2;      // issue S/dP of block i+1 before the dV/dK/dQ of block i
-    // dQ staging (fp32, [128][min(D,32)] boxes) aliases the P tile (and the dS tile when D = 128)
-    static constexpr int kDqBoxCols = kD >= 32 ? 32 : kD;
+    // dQ staging (16-bit, [128][min(D,64)] boxes, 128B swizzle when D >= 64) aliases the P tile
+    static constexpr int kDqBoxCols = kD >= 64 ? 64 : kD;
     static constexpr int kDqBoxes = kD / kDqBoxCols;
-    static constexpr int kDqBoxBytes = kBM * kDqBoxCols * 4;
+    static constexpr int kDqBoxBytes = kBM * kDqBoxCols * 2;
     static constexpr bool kDqAliasesDs = kDqBoxes * kDqBoxBytes > 2 * kHalfBytes;
     static constexpr int kK = 0;
     static constexpr int kV = kK + kTileBytes;
@@ -432,12 +432,17 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdKernelParams p) {
                     tmem_ld_n<kChunk>(tm_dq + c0, q);
                     tmem_ld_wait();
                     const int gcol = wg * C::kDqColsPerWg + c0;            // first dQ column of this chunk
-                    uint8_t* box = smem + C::kP + (gcol / C::kDqBoxCols) * C::kDqBoxBytes + r * (C::kDqBoxCols * 4);
+                    uint8_t* box = smem + C::kP + (gcol / C::kDqBoxCols) * C::kDqBoxBytes + r * (C::kDqBoxCols * 2);
 #pragma unroll
-                    for (int i = 0; i < kChunk; i += 4) {
-                        const int c16 = ((gcol % C::kDqBoxCols) + i) / 4;  // 16-byte chunk inside the box row
-                        const int off = (C::kDqBoxCols == 32) ? ((c16 ^ (r & 7)) << 4) : (c16 << 4);
-                        *reinterpret_cast<uint4*>(box + off) = make_uint4(q[i], q[i + 1], q[i + 2], q[i + 3]);
+                    for (int i = 0; i < kChunk; i += 8) {
+                        const int c16 = ((gcol % C::kDqBoxCols) + i) / 8;  // 16-byte chunk inside the box row
+                        const int off = (C::kDqBoxCols == 64) ? ((c16 ^ (r & 7)) << 4) : (c16 << 4);
+                        uint4 v;
+                        v.x = pack2<kBf16>(__uint_as_float(q[i + 0]), __uint_as_float(q[i + 1]));
+                        v.y = pack2<kBf16>(__uint_as_float(q[i + 2]), __uint_as_float(q[i + 3]));
+                        v.z = pack2<kBf16>(__uint_as_float(q[i + 4]), __uint_as_float(q[i + 5]));
+                        v.w = pack2<kBf16>(__uint_as_float(q[i + 6]), __uint_as_float(q[i + 7]));
+                        *reinterpret_cast<uint4*>(box + off) = v;
                     }
                 }
             }
@@ -447,16 +452,9 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdKernelParams p) {
             if (ctid == 0) {
                 mbar_arrive(dq_empty);
 #pragma unroll
-                for (int bx = 0; bx < C::kDqBoxes; ++bx) {
-                    asm volatile(
-                        "cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group"
-                        " [%0, {%2, %3, %4, %5}], [%1];"
-                        :
-                        : "l"(reinterpret_cast<uint64_t>(&p.map_dq)),
-                          "r"(smem_u32(smem + C::kP + bx * C::kDqBoxBytes)), "r"(bx * C::kDqBoxCols), "r"(mrow0),
-                          "r"(h), "r"(b)
-                        : "memory");
-                }
+                for (int bx = 0; bx < C::kDqBoxes; ++bx)
+                    tma_reduce_add_4d(&p.map_dq, smem + C::kP + bx * C::kDqBoxBytes, bx * C::kDqBoxCols, mrow0, h,
+                                      (nb % p.dq_groups) * p.B + b);
                 bulk_commit_group();
                 bulk_wait_group_read<0>();
             }
@@ -512,12 +510,12 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdKernelParams p) {
 // ------------------------------------------------------------------------------------------
 // helper kernels
 // ------------------------------------------------------------------------------------------
-// delta = rowsum(O * dO) in fp32 (reference: _bwd_preprocess :516-556) + zero the fp32 dQ accumulator.
+// delta = rowsum(O * dO) in fp32 (reference: _bwd_preprocess :516-556) + zero the 16-bit dQ group surface.
 template <int kD, bool kBf16>
 __global__ void attn_bwd_preprocess_kernel(const uint8_t* __restrict__ o, int64_t o_sb, int64_t o_sh, int64_t o_sm,
                                            const uint8_t* __restrict__ dout, int64_t do_sb, int64_t do_sh,
-                                           int64_t do_sm, float* __restrict__ delta, float* __restrict__ dq_acc, int B,
-                                           int H, int M) {
+                                           int64_t do_sm, float* __restrict__ delta, uint4* __restrict__ dq_ws,
+                                           int dq_groups, int B, int H, int M) {
     constexpr int kTpr = kD / 8;                              // threads per row, 8 elements (16 B) each
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t row = gid / kTpr;
@@ -540,9 +538,7 @@ __global__ void attn_bwd_preprocess_kernel(const uint8_t* __restrict__ o, int64_
             acc = fmaf(a.x, c.x, acc);
             acc = fmaf(a.y, c.y, acc);
         }
-        float4* z = reinterpret_cast<float4*>(dq_acc + row * kD + part * 8);
-        z[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-        z[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int g = 0; g < dq_groups; ++g) dq_ws[(g * rows + row) * kTpr + part] = make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int off = kTpr / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
@@ -550,24 +546,36 @@ __global__ void attn_bwd_preprocess_kernel(const uint8_t* __restrict__ o, int64_
 }
 
 template <int kD, bool kBf16>
-__global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ dq_acc, uint8_t* __restrict__ dq, int64_t sb,
-                                           int64_t sh, int64_t sm, int B, int H, int M, float scale) {
+__global__ void attn_bwd_dq_convert_kernel(const uint4* __restrict__ dq_ws, int dq_groups, uint8_t* __restrict__ dq,
+                                           int64_t sb, int64_t sh, int64_t sm, int B, int H, int M, float scale) {
     constexpr int kTpr = kD / 8;
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t row = gid / kTpr;
     const int part = static_cast<int>(gid % kTpr);
-    if (row >= (int64_t)B * H * M) return;
+    const int64_t rows = (int64_t)B * H * M;
+    if (row >= rows) return;
     const int m = static_cast<int>(row % M);
     const int64_t bh = row / M;
     const int hh = static_cast<int>(bh % H);
     const int64_t bb = bh / H;
-    const float4 a = *reinterpret_cast<const float4*>(dq_acc + row * kD + part * 8);
-    const float4 c = *reinterpret_cast<const float4*>(dq_acc + row * kD + part * 8 + 4);
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int g = 0; g < dq_groups; ++g) {
+        const uint4 u = __ldg(dq_ws + (g * rows + row) * kTpr + part);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 f = unpack2<kBf16>(w[e]);
+            acc[2 * e] += f.x;
+            acc[2 * e + 1] += f.y;
+        }
+    }
     uint4 out;
-    out.x = pack2<kBf16>(a.x * scale, a.y * scale);
-    out.y = pack2<kBf16>(a.z * scale, a.w * scale);
-    out.z = pack2<kBf16>(c.x * scale, c.y * scale);
-    out.w = pack2<kBf16>(c.z * scale, c.w * scale);
+    out.x = pack2<kBf16>(acc[0] * scale, acc[1] * scale);
+    out.y = pack2<kBf16>(acc[2] * scale, acc[3] * scale);
+    out.z = pack2<kBf16>(acc[4] * scale, acc[5] * scale);
+    out.w = pack2<kBf16>(acc[6] * scale, acc[7] * scale);
     *reinterpret_cast<uint4*>(dq + 2 * (bb * sb + hh * sh + m * sm + part * 8)) = out;
 }
 
@@ -698,15 +706,15 @@ cudaError_t launch_attn_bwd(const AttnBwdKernelParams& kp, int D, bool bf16, int
 }
 
 cudaError_t launch_attn_bwd_preprocess(const void* o, const int64_t* os, const void* dout, const int64_t* ds,
-                                       float* delta, float* dq_acc, int B, int H, int M, int D, bool bf16,
-                                       cudaStream_t stream) {
+                                       float* delta, void* dq_ws, int dq_groups, int B, int H, int M, int D,
+                                       bool bf16, cudaStream_t stream) {
     const int64_t threads = (int64_t)B * H * M * (D / 8);
     const int block = 256;
     const int grid = static_cast<int>((threads + block - 1) / block);
 #define B200T5_PRE(DD, BF)                                                                                         \
     attn_bwd_preprocess_kernel<DD, BF><<<grid, block, 0, stream>>>(                                                \
         static_cast<const uint8_t*>(o), os[0], os[1], os[2], static_cast<const uint8_t*>(dout), ds[0], ds[1],     \
-        ds[2], delta, dq_acc, B, H, M)
+        ds[2], delta, static_cast<uint4*>(dq_ws), dq_groups, B, H, M)
     switch (D) {
         case 16: if (bf16) B200T5_PRE(16, true); else B200T5_PRE(16, false); break;
         case 32: if (bf16) B200T5_PRE(32, true); else B200T5_PRE(32, false); break;
@@ -719,14 +727,15 @@ cudaError_t launch_attn_bwd_preprocess(const void* o, const int64_t* os, const v
     return cudaGetLastError();
 }
 
-cudaError_t launch_attn_bwd_dq_convert(const float* dq_acc, void* dq, const int64_t* s, int B, int H, int M, int D,
-                                       float sm_scale, bool bf16, cudaStream_t stream) {
+cudaError_t launch_attn_bwd_dq_convert(const void* dq_ws, int dq_groups, void* dq, const int64_t* s, int B, int H,
+                                       int M, int D, float sm_scale, bool bf16, cudaStream_t stream) {
     const int64_t threads = (int64_t)B * H * M * (D / 8);
     const int block = 256;
     const int grid = static_cast<int>((threads + block - 1) / block);
 #define B200T5_CVT(DD, BF)                                                                                  \
-    attn_bwd_dq_convert_kernel<DD, BF><<<grid, block, 0, stream>>>(dq_acc, static_cast<uint8_t*>(dq), s[0], \
-                                                                    s[1], s[2], B, H, M, sm_scale)
+    attn_bwd_dq_convert_kernel<DD, BF><<<grid, block, 0, stream>>>(static_cast<const uint4*>(dq_ws), dq_groups, \
+                                                                    static_cast<uint8_t*>(dq), s[0], s[1], s[2], B, \
+                                                                    H, M, sm_scale)
     switch (D) {
         case 16: if (bf16) B200T5_CVT(16, true); else B200T5_CVT(16, false); break;
         case 32: if (bf16) B200T5_CVT(32, true); else B200T5_CVT(32, false); break;

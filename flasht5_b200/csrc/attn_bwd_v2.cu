@@ -10,10 +10,10 @@
 //   tensor pipe (1 thread):  S,dP(k+1) | dV,dK(k) | dQ(k) | S,dP(k+2) | ...
 //   compute warpgroups:      [B] P,dS(k+1) in registers   (overlaps dV,dK,dQ(k) and S,dP(k+2))
 //                            [C] wait until dV,dK,dQ(k) have finished reading the P / dS tiles
+//                            [E] drain dQ(k) TMEM -> 16-bit staging tile (double buffered) -> TMA reduce-add
+//                                into the dQ group surface
 //                            [D] P,dS(k+1) -> shared memory (16-bit, 128B swizzle) -> signal the MMA thread,
 //                                dS tile -> global through TMA (reduce-add into the batch-group surface)
-//                            [E] drain dQ(k) TMEM -> fp32 staging tile -> TMA reduce-add into the accumulator
-//                                (overlaps dV,dK(k+1))
 //
 // The difference from attn_bwd.cu is the order of [B]..[E]: the dQ drain of block k is deferred until
 // after the math of block k+1, and it has its own staging tile, so the elementwise work no longer sits
@@ -44,9 +44,8 @@ struct Bwd2Cfg {
     static constexpr int kTileBytes = kBM * kD * 2;
     static constexpr uint32_t kSwizzle = kRowBytes == 128 ? kSwz128 : (kRowBytes == 64 ? kSwz64 : kSwz32);
     static constexpr int kQStages = 2;
-    static constexpr int kDqBoxCols = kD >= 32 ? 32 : kD;           // fp32 columns per staging box
-    static constexpr int kDqBoxes = kD / kDqBoxCols;
-    static constexpr int kDqBoxBytes = kBM * kDqBoxCols * 4;
+    // dQ staging: one [128][D] tile in the io dtype (128B swizzle at D = 64, linear below), double buffered
+    static constexpr int kDqStageBytes = kBM * kD * 2;
     static constexpr int kDqColsPerWg = kD >= 32 ? kD / 2 : kD;     // D = 16: warpgroup 0 drains everything
     static constexpr int kK = 0;
     static constexpr int kV = kK + kTileBytes;
@@ -56,7 +55,7 @@ struct Bwd2Cfg {
     static constexpr int kP = kBias + 2 * kHalfBytes;
     static constexpr int kDS = kP + 2 * kHalfBytes;
     static constexpr int kDQ = kDS + 2 * kHalfBytes;
-    static constexpr int kBars = kDQ + kDqBoxes * kDqBoxBytes;
+    static constexpr int kBars = kDQ + 2 * kDqStageBytes;
     static constexpr int kNumBars = 1 + 2 * kQStages + 4 + 5;
     static constexpr int kTmemSlot = kBars + kNumBars * 8;
     static constexpr int kTotal = kTmemSlot + 16;
@@ -301,31 +300,35 @@ attn_bwd_kernel_v2(const __grid_constant__ AttnBwdKernelParams p) {
         const float scale_log2 = p.sm_scale * kLog2e;
         const int64_t stat_base = ((int64_t)b * p.H + h) * p.M;
 
-        // dQ(kq) : TMEM -> swizzled fp32 staging tile (my 32 / 16 columns of my row)
-        auto drain_dq = [&]() {
+        // dQ : TMEM -> 16-bit staging tile `buf` (my 32 / 16 columns of my row)
+        auto drain_dq = [&](int buf) {
             if (wg == 0 || kD >= 32) {
                 constexpr int kCols = C::kDqColsPerWg;
                 constexpr int kChunk = kCols >= 32 ? 32 : kCols;
+                uint8_t* row_base = smem + C::kDQ + buf * C::kDqStageBytes + r * (kD * 2);
 #pragma unroll
                 for (int c0 = 0; c0 < kCols; c0 += kChunk) {
                     uint32_t q[kChunk];
                     tmem_ld_cols<kChunk>(tm_dq + c0, q);
                     tmem_ld_wait();
                     const int gcol = wg * C::kDqColsPerWg + c0;            // first dQ column of this chunk
-                    uint8_t* box = smem + C::kDQ + (gcol / C::kDqBoxCols) * C::kDqBoxBytes + r * (C::kDqBoxCols * 4);
 #pragma unroll
-                    for (int i = 0; i < kChunk; i += 4) {
-                        const int c16 = ((gcol % C::kDqBoxCols) + i) / 4;  // 16-byte chunk inside the box row
-                        const int off = (C::kDqBoxCols == 32) ? ((c16 ^ (r & 7)) << 4) : (c16 << 4);
-                        *reinterpret_cast<uint4*>(box + off) = make_uint4(q[i], q[i + 1], q[i + 2], q[i + 3]);
+                    for (int i = 0; i < kChunk; i += 8) {
+                        const int c16 = (gcol + i) / 8;                    // 16-byte chunk inside the row
+                        const int off = (kD == 64) ? ((c16 ^ (r & 7)) << 4) : (c16 << 4);
+                        uint4 v;
+                        v.x = pack2<kBf16>(__uint_as_float(q[i + 0]), __uint_as_float(q[i + 1]));
+                        v.y = pack2<kBf16>(__uint_as_float(q[i + 2]), __uint_as_float(q[i + 3]));
+                        v.z = pack2<kBf16>(__uint_as_float(q[i + 4]), __uint_as_float(q[i + 5]));
+                        v.w = pack2<kBf16>(__uint_as_float(q[i + 6]), __uint_as_float(q[i + 7]));
+                        *reinterpret_cast<uint4*>(row_base + off) = v;
                     }
                 }
             }
         };
-        auto issue_dq_reduce = [&](int mrow0) {
-#pragma unroll
-            for (int bx = 0; bx < C::kDqBoxes; ++bx)
-                tma_reduce_add_4d(&p.map_dq, smem + C::kDQ + bx * C::kDqBoxBytes, bx * C::kDqBoxCols, mrow0, h, b);
+        const int dq_c3 = (nb % p.dq_groups) * p.B + b;      // (group, batch) slice of the dQ surface
+        auto issue_dq_reduce = [&](int buf, int mrow0) {
+            tma_reduce_add_4d(&p.map_dq, smem + C::kDQ + buf * C::kDqStageBytes, 0, mrow0, h, dq_c3);
             bulk_commit_group();
         };
 
@@ -412,6 +415,20 @@ attn_bwd_kernel_v2(const __grid_constant__ AttnBwdKernelParams p) {
                 tc_fence_after();
             }
 
+            // ---------------- [E] drain dQ of the previous block (its MMAs completed at [C]) ----------------
+            // Staging buffer (k-1)&1 was last read by the TMA reduce of dQ(k-3), certified at barrier 2 of the
+            // previous iteration; the dS tile was last read by the TMA reduce of dS(k-1), issued one whole
+            // [B] ago -- thread 0 waits for it here so that [D] below may overwrite the tile.
+            if (k > 0) drain_dq((k - 1) & 1);
+            tc_fence_before();
+            fence_proxy_async_smem();
+            if (ctid == 0) bulk_wait_group_read<0>();
+            named_bar_sync(2, 256);
+            if (ctid == 0 && k > 0) {
+                mbar_arrive(dq_empty);                       // TMEM dQ columns are free for block k
+                issue_dq_reduce((k - 1) & 1, mrow0 - kBM);
+            }
+
             // ---------------- [D] P, dS -> shared memory; hand over to the MMA thread; dS tile -> global -----
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
@@ -425,7 +442,6 @@ attn_bwd_kernel_v2(const __grid_constant__ AttnBwdKernelParams p) {
                 }
             }
             fence_proxy_async_smem();
-            if (ctid == 0) bulk_wait_group_read<0>();        // staging tile: the TMA reduce of dQ(k-2) has read it
             named_bar_sync(1, 256);
             if (ctid == 0) {
                 mbar_arrive(pds_full);
@@ -440,30 +456,17 @@ attn_bwd_kernel_v2(const __grid_constant__ AttnBwdKernelParams p) {
                     bulk_commit_group();
                 }
             }
-
-            // ---------------- [E] drain dQ of the previous block (its MMAs completed at [C]) ----------------
-            if (k > 0) drain_dq();
-            tc_fence_before();
-            fence_proxy_async_smem();
-            if (ctid == 0) bulk_wait_group_read<0>();        // the dS tile has been read: [D] of block k+1 may overwrite it
-            named_bar_sync(2, 256);
-            if (ctid == 0 && k > 0) {
-                mbar_arrive(dq_empty);                       // TMEM dQ columns are free for block k
-                issue_dq_reduce(mrow0 - kBM);
-            }
         }
 
         // ---- tail: dQ of the last block, then dV (warpgroup 0) and dK * sm_scale (warpgroup 1) ----
         if (n_iter > 0) {
             mbar_wait(dq_full, (n_iter - 1) & 1);            // every MMA of this CTA has completed
             tc_fence_after();
-            if (ctid == 0) bulk_wait_group_read<0>();
-            named_bar_sync(1, 256);
-            drain_dq();
+            drain_dq((n_iter - 1) & 1);                      // that buffer's last reader was certified at barrier 2
             tc_fence_before();
             fence_proxy_async_smem();
             named_bar_sync(2, 256);
-            if (ctid == 0) issue_dq_reduce((i_start + n_iter - 1) * kBM);
+            if (ctid == 0) issue_dq_reduce((n_iter - 1) & 1, (i_start + n_iter - 1) * kBM);
         }
         {
             const int gn = col0 + r;

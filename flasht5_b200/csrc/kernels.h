@@ -31,7 +31,7 @@ struct AttnBwdKernelParams {
     CUtensorMap map_do;     // (D, M, H, B)
     CUtensorMap map_bias;   // (N, M, Hb, Bb)                                 [bias mode 1]
     CUtensorMap map_ds;     // (N, M, H, B) 16-bit dS workspace, row pitch = N rounded up to 8   [bias modes 1, 2]
-    CUtensorMap map_dq;     // fp32 accumulator (D, M, H, B), box (min(D,32), 128, 1, 1), reduce-add
+    CUtensorMap map_dq;     // 16-bit dQ group surface (D, M, H, dq_groups * B), box (min(D,64), 128, 1, 1), reduce-add
     const void* bias;       // [bias mode 2]
     int64_t bias_sb, bias_sh, bias_sm, bias_sn;
     void* dk;
@@ -47,6 +47,9 @@ struct AttnBwdKernelParams {
     // dS surface: (N, M, H, ds_groups) 16-bit.  Batch b adds its tile into group b % ds_groups with a TMA
     // reduce-add (ds_use_reduce = 1, surface pre-zeroed) or owns its slice and stores (ds_use_reduce = 0).
     int ds_groups, ds_use_reduce;
+    // dQ surface: key block nb adds its partial dQ tile (rounded to the io dtype) into group nb % dq_groups;
+    // groups hold <= 4 key blocks each and are summed in fp32 by the convert kernel.
+    int dq_groups;
 };
 
 cudaError_t launch_attn_fwd(const AttnFwdKernelParams& kp, int D, bool bf16, int bias_mode, bool causal,
@@ -56,13 +59,13 @@ cudaError_t launch_attn_bwd(const AttnBwdKernelParams& kp, int D, bool bf16, int
 cudaError_t launch_attn_bwd_v2(const AttnBwdKernelParams& kp, int D, bool bf16, int bias_mode, bool causal,
                                cudaStream_t stream);
 
-// delta[b,h,m] = sum_d O*dO  (fp32); also zero-fills the fp32 dQ accumulator.
+// delta[b,h,m] = sum_d O*dO  (fp32); also zero-fills the 16-bit dQ group surface (dq_groups, B, H, M, D).
 cudaError_t launch_attn_bwd_preprocess(const void* o, const int64_t* o_strides, const void* dout,
-                                       const int64_t* do_strides, float* delta, float* dq_acc, int B, int H, int M,
-                                       int D, bool bf16, cudaStream_t stream);
-// dq[b,h,m,:] = 16bit(dq_acc * sm_scale)
-cudaError_t launch_attn_bwd_dq_convert(const float* dq_acc, void* dq, const int64_t* dq_strides, int B, int H, int M,
-                                       int D, float sm_scale, bool bf16, cudaStream_t stream);
+                                       const int64_t* do_strides, float* delta, void* dq_ws, int dq_groups, int B,
+                                       int H, int M, int D, bool bf16, cudaStream_t stream);
+// dq[b,h,m,:] = 16bit(sm_scale * sum_g dq_ws[g,b,h,m,:])
+cudaError_t launch_attn_bwd_dq_convert(const void* dq_ws, int dq_groups, void* dq, const int64_t* dq_strides, int B,
+                                       int H, int M, int D, float sm_scale, bool bf16, cudaStream_t stream);
 // dbias[bb,hb,m,n] = sum over broadcast batch/head of ds_ws[b,h,m,n]; causal-masked entries are 0 (never read).
 cudaError_t launch_dbias_reduce(const void* ds_ws, int ws_pitch, void* dbias, const int64_t* dbias_strides, int B, int H,
                                 int M, int N, int reduce_b, int reduce_h, bool causal, bool bf16, cudaStream_t stream);

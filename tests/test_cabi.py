@@ -65,7 +65,7 @@ def test_workspace_size_queries_need_no_gpu(lib):
     p.bias = None
     no_bias = lib.b200t5_attn_bwd_workspace_bytes(C.byref(p))
     rows = 2 * 3 * 100
-    assert no_bias >= rows * 4 + rows * 64 * 4
+    assert no_bias >= rows * 4 + rows * 64 * 2      # delta (fp32) + one 16-bit dQ group
     p.bias = 16                                     # any non-NULL pointer: size only depends on presence
     with_bias = lib.b200t5_attn_bwd_workspace_bytes(C.byref(p))
     assert with_bias >= no_bias + rows * 80 * 2      # dS rows padded to a multiple of 8 columns

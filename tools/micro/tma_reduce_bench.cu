@@ -62,10 +62,11 @@ float run(uint8_t* dst, size_t surface, int chunk, int iters, int tile, int grid
 int main() {
     const size_t surface = 32u << 20;           // 32 MiB: L2 resident (like the fp32 dBias of the headline shape)
     uint8_t* dst; cudaMalloc(&dst, surface); cudaMemset(dst, 0, surface);
-    const int iters = 64, grid = 148 * 4;
+    const int iters = 64;
+    for (int grid : {37 * 4, 74 * 4, 148, 148 * 2, 148 * 4, 148 * 8}) {
     const char* names[4] = {"bulk add.f32", "bulk add.bf16", "bulk store", "red.v4.f32"};
-    for (int tile : {16384, 65536}) {
-        for (int chunk : {512, 2048, 16384}) {
+    for (int tile : {16384}) {
+        for (int chunk : {16384}) {
             if (chunk > tile) continue;
             float ms[4];
             ms[0] = run<0>(dst, surface, chunk, iters, tile, grid);
@@ -77,6 +78,7 @@ int main() {
             for (int m = 0; m < 4; ++m) printf("  %s %.0f GB/s", names[m], bytes / ms[m] / 1e6);
             printf("\n");
         }
+    }
     }
     return 0;
 }
