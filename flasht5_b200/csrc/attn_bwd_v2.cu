@@ -98,6 +98,16 @@ __device__ __forceinline__ void p_ds_chunk(const uint32_t (&sr)[32], const uint3
 
 }  // namespace
 
+#ifdef B200T5_BWD_TIMING
+__device__ long long g_bwd_ts[2][16][8];      // [role][iteration][slot]
+#define BWD_TS(role, k, slot)                                                          \
+    do {                                                                               \
+        if (blockIdx.x == 777 && (k) < 16) g_bwd_ts[role][k][slot] = clock64();        \
+    } while (0)
+#else
+#define BWD_TS(role, k, slot) do { } while (0)
+#endif
+
 template <int kD, bool kBf16, int kBiasMode, bool kCausal>
 __global__ void __launch_bounds__(384, 1)
 attn_bwd_kernel_v2(const __grid_constant__ AttnBwdKernelParams p) {
@@ -201,16 +211,26 @@ attn_bwd_kernel_v2(const __grid_constant__ AttnBwdKernelParams p) {
                                 bb);
                 }
             }
-        } else if (warp == 5 && lane == 0 && n_iter > 0) {
-            // ---- MMA issuer ----
+        } else if (warp == 5 && n_iter > 0) {
+            // ---- MMA issuer: the whole warp runs the loop (descriptor arithmetic stays warp-uniform), one
+            //      elected lane issues the tcgen05 instructions ----
+            const bool leader = elect_one();
             constexpr uint32_t idesc_s = make_idesc(kBf16, 128, 128, false, false);    // S, dP
             constexpr uint32_t idesc_dkv = make_idesc(kBf16, 128, kD, true, true);     // dV, dK
             constexpr uint32_t idesc_dq = make_idesc(kBf16, 128, kD, false, true);     // dQ
             constexpr uint32_t sbo = 8 * C::kRowBytes;
-            const uint32_t k_addr = smem_u32(smem + C::kK);
-            const uint32_t v_addr = smem_u32(smem + C::kV);
-            const uint32_t p_addr = smem_u32(smem + C::kP);
-            const uint32_t ds_addr = smem_u32(smem + C::kDS);
+            constexpr uint32_t hi_op = sdesc_hi(sbo, C::kSwizzle);       // Q, dO, K, V tiles (either major)
+            constexpr uint32_t hi_pds = sdesc_hi(1024, kSwz128);         // P, dS tiles (either major)
+            const uint32_t k_lo = sdesc_lo(smem_u32(smem + C::kK), 16);           // K-major (S)
+            const uint32_t v_lo = sdesc_lo(smem_u32(smem + C::kV), 16);           // K-major (dP)
+            const uint32_t k_mn_lo = sdesc_lo(smem_u32(smem + C::kK), C::kTileBytes);   // MN-major (dQ)
+            const uint32_t q_lo0 = sdesc_lo(smem_u32(smem + C::kQ), 16);
+            const uint32_t do_lo0 = sdesc_lo(smem_u32(smem + C::kDO), 16);
+            const uint32_t q_mn_lo0 = sdesc_lo(smem_u32(smem + C::kQ), C::kTileBytes);
+            const uint32_t do_mn_lo0 = sdesc_lo(smem_u32(smem + C::kDO), C::kTileBytes);
+            const uint32_t p_mn_lo = sdesc_lo(smem_u32(smem + C::kP), kHalfBytes);      // A = P^T  (MN-major)
+            const uint32_t ds_mn_lo = sdesc_lo(smem_u32(smem + C::kDS), kHalfBytes);    // A = dS^T (MN-major)
+            const uint32_t ds_k_lo = sdesc_lo(smem_u32(smem + C::kDS), 16);             // A = dS   (K-major)
             const uint32_t tm_s = tmem_base + C::kColS;
             const uint32_t tm_dp = tmem_base + C::kColDP;
             const uint32_t tm_dv = tmem_base + C::kColDV;
@@ -218,45 +238,48 @@ attn_bwd_kernel_v2(const __grid_constant__ AttnBwdKernelParams p) {
             const uint32_t tm_dq = tmem_base + C::kColDQ;
 
             auto issue_s_dp = [&](int k) {
-                const int s = k % C::kQStages;
-                const uint32_t q_addr = smem_u32(smem + C::kQ + s * C::kTileBytes);
-                const uint32_t do_addr = smem_u32(smem + C::kDO + s * C::kTileBytes);
+                const uint32_t so = (k % C::kQStages) * (C::kTileBytes >> 4);
+                if (leader) {
 #pragma unroll
-                for (int kk = 0; kk < kD / 16; ++kk)
-                    umma_ss(tm_s, make_sdesc(q_addr + kk * 32, 16, sbo, C::kSwizzle),
-                            make_sdesc(k_addr + kk * 32, 16, sbo, C::kSwizzle), idesc_s, kk > 0 ? 1u : 0u);
+                    for (int kk = 0; kk < kD / 16; ++kk)
+                        umma_ss2(tm_s, q_lo0 + so + kk * 2, hi_op, k_lo + kk * 2, hi_op, idesc_s, kk > 0 ? 1u : 0u);
 #pragma unroll
-                for (int kk = 0; kk < kD / 16; ++kk)
-                    umma_ss(tm_dp, make_sdesc(do_addr + kk * 32, 16, sbo, C::kSwizzle),
-                            make_sdesc(v_addr + kk * 32, 16, sbo, C::kSwizzle), idesc_s, kk > 0 ? 1u : 0u);
-                umma_commit(sdp_full);
+                    for (int kk = 0; kk < kD / 16; ++kk)
+                        umma_ss2(tm_dp, do_lo0 + so + kk * 2, hi_op, v_lo + kk * 2, hi_op, idesc_s, kk > 0 ? 1u : 0u);
+                    umma_commit(sdp_full);
+                }
+                __syncwarp();
             };
             auto issue_dv_dk = [&](int k) {
                 const int s = k % C::kQStages;
-                const uint32_t q_addr = smem_u32(smem + C::kQ + s * C::kTileBytes);
-                const uint32_t do_addr = smem_u32(smem + C::kDO + s * C::kTileBytes);
+                const uint32_t so = s * (C::kTileBytes >> 4);
                 const uint32_t acc = k > 0 ? 1u : 0u;
-                // dV += P^T dO ; dK += dS^T Q      (K dimension = the 128 query rows of this block)
+                if (leader) {
+                    // dV += P^T dO ; dK += dS^T Q      (K dimension = the 128 query rows of this block)
 #pragma unroll
-                for (int kk = 0; kk < kBM / 16; ++kk)
-                    umma_ss(tm_dv, make_sdesc(p_addr + kk * 2048, kHalfBytes, 1024, kSwz128),
-                            make_sdesc(do_addr + kk * 16 * C::kRowBytes, C::kTileBytes, sbo, C::kSwizzle), idesc_dkv,
-                            (acc | (kk > 0)) ? 1u : 0u);
+                    for (int kk = 0; kk < kBM / 16; ++kk)
+                        umma_ss2(tm_dv, p_mn_lo + kk * (2048 >> 4), hi_pds,
+                                 do_mn_lo0 + so + ((kk * 16 * C::kRowBytes) >> 4), hi_op, idesc_dkv,
+                                 (acc | (kk > 0)) ? 1u : 0u);
 #pragma unroll
-                for (int kk = 0; kk < kBM / 16; ++kk)
-                    umma_ss(tm_dk, make_sdesc(ds_addr + kk * 2048, kHalfBytes, 1024, kSwz128),
-                            make_sdesc(q_addr + kk * 16 * C::kRowBytes, C::kTileBytes, sbo, C::kSwizzle), idesc_dkv,
-                            (acc | (kk > 0)) ? 1u : 0u);
-                umma_commit(qdo_empty + s);
+                    for (int kk = 0; kk < kBM / 16; ++kk)
+                        umma_ss2(tm_dk, ds_mn_lo + kk * (2048 >> 4), hi_pds,
+                                 q_mn_lo0 + so + ((kk * 16 * C::kRowBytes) >> 4), hi_op, idesc_dkv,
+                                 (acc | (kk > 0)) ? 1u : 0u);
+                    umma_commit(qdo_empty + s);
+                }
+                __syncwarp();
             };
             auto issue_dq = [&]() {
-                // dQ_blk = dS K                    (K dimension = the 128 keys of this CTA)
+                if (leader) {
+                    // dQ_blk = dS K                    (K dimension = the 128 keys of this CTA)
 #pragma unroll
-                for (int kk = 0; kk < kBN / 16; ++kk)
-                    umma_ss(tm_dq, make_sdesc(ds_addr + (kk / 4) * kHalfBytes + (kk % 4) * 32, 16, 1024, kSwz128),
-                            make_sdesc(k_addr + kk * 16 * C::kRowBytes, C::kTileBytes, sbo, C::kSwizzle), idesc_dq,
-                            kk > 0 ? 1u : 0u);
-                umma_commit(dq_full);
+                    for (int kk = 0; kk < kBN / 16; ++kk)
+                        umma_ss2(tm_dq, ds_k_lo + (((kk / 4) * kHalfBytes + (kk % 4) * 32) >> 4), hi_pds,
+                                 k_mn_lo + ((kk * 16 * C::kRowBytes) >> 4), hi_op, idesc_dq, kk > 0 ? 1u : 0u);
+                    umma_commit(dq_full);
+                }
+                __syncwarp();
             };
 
             mbar_wait(kv_full, 0);
@@ -271,14 +294,18 @@ attn_bwd_kernel_v2(const __grid_constant__ AttnBwdKernelParams p) {
                     tc_fence_after();
                     issue_s_dp(kn);
                 }
+                if (lane == 0) BWD_TS(1, k, 0);
                 mbar_wait(pds_full, k & 1);
                 tc_fence_after();
+                if (lane == 0) BWD_TS(1, k, 1);
                 issue_dv_dk(k);
                 if (k > 0) {
                     mbar_wait(dq_empty, (k - 1) & 1);    // dQ(k-1) has been drained out of TMEM
                     tc_fence_after();
                 }
+                if (lane == 0) BWD_TS(1, k, 2);
                 issue_dq();
+                if (lane == 0) BWD_TS(1, k, 3);
             }
         }
     } else {
@@ -358,8 +385,10 @@ attn_bwd_kernel_v2(const __grid_constant__ AttnBwdKernelParams p) {
             const bool need_mask = (col0 + kBN > p.N) || (kCausal && (col0 + kBN - 1 > mrow0 + pseq));
 
             // ---------------- [B] P and dS of this block, in registers ----------------
+            if (ctid == 0) BWD_TS(0, k, 0);
             mbar_wait(sdp_full, k & 1);
             tc_fence_after();
+            if (ctid == 0) BWD_TS(0, k, 1);
             if (kBiasMode == 1) mbar_wait(b_full + wg, k & 1);
             uint32_t pp[2][16], dd[2][16];
 #pragma unroll
@@ -410,10 +439,12 @@ attn_bwd_kernel_v2(const __grid_constant__ AttnBwdKernelParams p) {
             }
 
             // ---------------- [C] the previous block's dV / dK / dQ MMAs are done with the P / dS tiles ------
+            if (ctid == 0) BWD_TS(0, k, 2);
             if (k > 0) {
                 mbar_wait(dq_full, (k - 1) & 1);
                 tc_fence_after();
             }
+            if (ctid == 0) BWD_TS(0, k, 3);
 
             // ---------------- [E] drain dQ of the previous block (its MMAs completed at [C]) ----------------
             // Staging buffer (k-1)&1 was last read by the TMA reduce of dQ(k-3), certified at barrier 2 of the
@@ -422,8 +453,11 @@ attn_bwd_kernel_v2(const __grid_constant__ AttnBwdKernelParams p) {
             if (k > 0) drain_dq((k - 1) & 1);
             tc_fence_before();
             fence_proxy_async_smem();
+            if (ctid == 0) BWD_TS(0, k, 4);
             if (ctid == 0) bulk_wait_group_read<0>();
+            if (ctid == 0) BWD_TS(0, k, 5);
             named_bar_sync(2, 256);
+            if (ctid == 0) BWD_TS(0, k, 6);
             if (ctid == 0 && k > 0) {
                 mbar_arrive(dq_empty);                       // TMEM dQ columns are free for block k
                 issue_dq_reduce((k - 1) & 1, mrow0 - kBM);
@@ -443,6 +477,7 @@ attn_bwd_kernel_v2(const __grid_constant__ AttnBwdKernelParams p) {
             }
             fence_proxy_async_smem();
             named_bar_sync(1, 256);
+            if (ctid == 0) BWD_TS(0, k, 7);
             if (ctid == 0) {
                 mbar_arrive(pds_full);
                 if (kBiasMode != 0) {
@@ -523,6 +558,26 @@ static cudaError_t launch_bwd2_inst(const AttnBwdKernelParams& kp, cudaStream_t 
     const int grid = kp.B * kp.H * kp.num_n_blocks;
     kern<<<grid, 384, C::kTotal, stream>>>(kp);
     count_launch();
+#ifdef B200T5_BWD_TIMING
+    {
+        cudaDeviceSynchronize();
+        long long ts[2][16][8];
+        cudaMemcpyFromSymbol(ts, g_bwd_ts, sizeof(ts));
+        const long long t0 = ts[0][0][0];
+        printf("compute thread 0 (cycles rel. to first stamp): k: [B wait-start, B start, B end, C end, E drained, tma-wait end, bar2, bar1]\n");
+        for (int k = 0; k < 8; ++k) {
+            printf(" k=%d:", k);
+            for (int j = 0; j < 8; ++j) printf(" %7lld", ts[0][k][j] - t0);
+            printf("\n");
+        }
+        printf("mma thread: k: [wait pds_full start, pds_full, after dq_empty, issued dq]\n");
+        for (int k = 0; k < 8; ++k) {
+            printf(" k=%d:", k);
+            for (int j = 0; j < 4; ++j) printf(" %7lld", ts[1][k][j] - t0);
+            printf("\n");
+        }
+    }
+#endif
     return cudaGetLastError();
 }
 

@@ -180,28 +180,35 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdKernelParams p) {
                 tma_load_4d(smem + L::kBias + s * kBiasHalfBytes, &p.map_bias, bars.b_full + s,
                             (it >> 1) * kBN + (it & 1) * 64, row0, hb, bb);
             }
-        } else if (warp == 5 && lane == 0 && num_tiles > 0) {
-            // ---- MMA issuer ----
+        } else if (warp == 5 && num_tiles > 0) {
+            // ---- MMA issuer: the whole warp runs the loop (descriptor arithmetic stays warp-uniform), one
+            //      elected lane issues the tcgen05 instructions ----
+            const bool leader = elect_one();
             constexpr uint32_t idesc_s = make_idesc(kBf16, kBM, kBN, false, false);
             constexpr uint32_t idesc_pv = make_idesc(kBf16, kBM, kD, false, true);
             constexpr uint32_t sbo = 8 * L::kRowBytes;
-            const uint32_t q_addr = smem_u32(smem + L::kQ);
+            constexpr uint32_t hi_k = sdesc_hi(sbo, L::kSwizzle);          // Q, K (K-major) and V (MN-major) share it
+            const uint32_t q_lo = sdesc_lo(smem_u32(smem + L::kQ), 16);
+            const uint32_t k_lo0 = sdesc_lo(smem_u32(smem + L::kK), 16);
+            const uint32_t v_lo0 = sdesc_lo(smem_u32(smem + L::kV), L::kBoxBytes);
             const uint32_t tm_s = tmem_base;
             const uint32_t tm_o = tmem_base + L::kOCol;
             const uint32_t tm_p = tmem_base + L::kPCol;
 
             auto issue_s = [&](int j) {
                 const int s = j % kKVStages;
-                const uint32_t k_addr = smem_u32(smem + L::kK + s * L::kTileBytes);
+                const uint32_t k_lo = k_lo0 + s * (L::kTileBytes >> 4);
+                if (leader) {
 #pragma unroll
-                for (int kk = 0; kk < kD / 16; ++kk) {
-                    // K-major operands: 16 elements of K per MMA = 32 bytes inside a swizzled row
-                    const uint32_t off = (kk / 4) * L::kBoxBytes + (kk % 4) * 32;
-                    umma_ss(tm_s, make_sdesc(q_addr + off, 16, sbo, L::kSwizzle),
-                            make_sdesc(k_addr + off, 16, sbo, L::kSwizzle), idesc_s, kk > 0 ? 1u : 0u);
+                    for (int kk = 0; kk < kD / 16; ++kk) {
+                        // K-major operands: 16 elements of K per MMA = 32 bytes inside a swizzled row
+                        const uint32_t off = ((kk / 4) * L::kBoxBytes + (kk % 4) * 32) >> 4;
+                        umma_ss2(tm_s, q_lo + off, hi_k, k_lo + off, hi_k, idesc_s, kk > 0 ? 1u : 0u);
+                    }
+                    umma_commit(bars.s_full);
+                    umma_commit(bars.k_empty + s);
                 }
-                umma_commit(bars.s_full);
-                umma_commit(bars.k_empty + s);
+                __syncwarp();
             };
 
             mbar_wait(bars.q_full, 0);
@@ -220,16 +227,18 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdKernelParams p) {
                 mbar_wait(bars.v_full + s, (j / kKVStages) & 1);
                 mbar_wait(bars.p_full, j & 1);
                 tc_fence_after();
-                const uint32_t v_addr = smem_u32(smem + L::kV + s * L::kTileBytes);
+                const uint32_t v_lo = v_lo0 + s * (L::kTileBytes >> 4);
+                if (leader) {
 #pragma unroll
-                for (int kk = 0; kk < kBN / 16; ++kk) {
-                    // B = V, MN-major: 16 key rows per MMA; LBO = stride between 64-wide d chunks
-                    umma_ts(tm_o, tm_p + kk * 8,
-                            make_sdesc(v_addr + kk * 16 * L::kRowBytes, L::kBoxBytes, sbo, L::kSwizzle), idesc_pv,
-                            (j > 0 || kk > 0) ? 1u : 0u);
+                    for (int kk = 0; kk < kBN / 16; ++kk) {
+                        // B = V, MN-major: 16 key rows per MMA; LBO = stride between 64-wide d chunks
+                        umma_ts2(tm_o, tm_p + kk * 8, v_lo + ((kk * 16 * L::kRowBytes) >> 4), hi_k, idesc_pv,
+                                 (j > 0 || kk > 0) ? 1u : 0u);
+                    }
+                    umma_commit(bars.pv_done);
+                    umma_commit(bars.v_empty + s);
                 }
-                umma_commit(bars.pv_done);
-                umma_commit(bars.v_empty + s);
+                __syncwarp();
             }
         }
     } else {
