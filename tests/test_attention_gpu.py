@@ -19,6 +19,7 @@ import numpy as np
 import pytest
 import torch
 
+import flasht5_b200  # noqa: F401  (registers torch.ops.b200t5.*)
 from conftest import GOLDEN
 from oracle import attn_bias_ref as orc
 
@@ -240,8 +241,9 @@ def test_cuda_graph_capture_and_replay():
     assert torch.equal(o, o_ref) and torch.equal(L, L_ref)
     for a, b_ in zip(grads[1:3], g_ref[1:3]):                   # dK, dV are deterministic
         assert torch.equal(a, b_)
-    for a, b_ in ((grads[0], g_ref[0]), (grads[3], g_ref[3])):  # dQ: fp32 reduce-add order may differ
-        assert torch.allclose(a.float(), b_.float(), atol=2e-2, rtol=2e-2)
+    for a, b_ in ((grads[0], g_ref[0]), (grads[3], g_ref[3])):  # dQ, dBias: L2 reduce-add order may differ
+        mx, rf = orc.error_metrics(a, b_.float())
+        assert rf < 4e-3, (mx, rf)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -280,7 +282,10 @@ def test_full_size_backward_properties():
     dq5, dk5, dv5, db5 = torch.ops.b200t5.attn_bias_bwd(o5, do[sl], q[sl], k[sl], v[sl], bias, L5, False, 1.0)
     assert torch.equal(o5, o[sl]) and torch.equal(L5, L[sl])
     assert torch.equal(dk5, dk[sl]) and torch.equal(dv5, dv[sl])
-    assert torch.allclose(dq5.float(), dq[sl].float(), atol=3e-2, rtol=2e-2)
+    # dQ partial tiles are reduce-added at L2 in the io dtype: the arrival order of the key blocks may differ
+    # between launches, so dQ is reproducible to a 16-bit rounding of the partial sums, not bitwise
+    mx, rf = orc.error_metrics(dq5, dq[sl].float())
+    assert rf < 4e-3, (mx, rf)
     # (2) dBias additivity: sum of per-half-batch dBias == full-batch dBias (up to 16-bit rounding)
     halves = []
     for s0 in (slice(0, 16), slice(16, 32)):
