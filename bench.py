@@ -182,7 +182,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from flasht5_b200 import _cabi, flash_attention_v2_bias
-    from flasht5_b200.data_parallel import allreduce_dbias
+    from flasht5_b200.data_parallel import allreduce_dbias, allreduce_dbias_overlapped
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -222,11 +222,15 @@ def run_ours(args):
         o, L = torch.ops.b200t5.attn_bias_fwd(q, k, v, bias, False, SM_SCALE)
         dq, dk, dv, ds = torch.ops.b200t5.attn_bias_bwd(o, do, q, k, v, bias, L, False, SM_SCALE)
         if world > 1:
-            ds = allreduce_dbias(ds)
+            # the one exchange of the path: dBias summed over ranks (fp32), overlapped with the next step's kernels
+            ds = allreduce_dbias_overlapped(ds, comm_stream)
         return o, dq, dk, dv, ds
+
+    comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
 
     def barrier():
         if world > 1:
+            torch.cuda.current_stream(dev).wait_stream(comm_stream)
             dist.barrier()
         torch.cuda.synchronize()
 
@@ -245,6 +249,8 @@ def run_ours(args):
     ev0.record()
     for i in range(args.steps):
         step(i)
+    if world > 1:
+        torch.cuda.current_stream(dev).wait_stream(comm_stream)     # every all-reduce is inside the timed region
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
@@ -364,7 +370,8 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": WB * world, "seq_len": WS, "parallelism": "dp%d" % world,
                        "l2": "inputs rotate over %d buffer sets of 185 MB each (> 126 MB L2)" % NSETS,
-                       "exchange": "fp32 NCCL all-reduce of dBias per step" if world > 1 else "none"},
+                       "exchange": "fp32 NCCL all-reduce of dBias every step on a side stream (overlaps the next step's "
+                                   "kernels; all of them complete inside the timed region)" if world > 1 else "none"},
             "tokens_per_s": world * B * S / (ms_step * 1e-3),
             "frac_of_peak": value / (world * peak), "peak_tflops_per_gpu": peak, "peak_source": peak_src,
             "gpu_launches": int(launches), "launches_per_step": launches / args.steps,

@@ -12,7 +12,7 @@ from typing import Optional, Tuple
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_batch", "allreduce_dbias"]
+__all__ = ["shard_batch", "allreduce_dbias", "allreduce_dbias_overlapped"]
 
 
 def shard_batch(global_batch: int, rank: int, world_size: int) -> Tuple[int, int]:
@@ -34,3 +34,19 @@ def allreduce_dbias(dbias: Optional[torch.Tensor], group=None) -> Optional[torch
     acc = dbias.float()
     dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
     return acc.to(dbias.dtype)
+
+
+def allreduce_dbias_overlapped(dbias: Optional[torch.Tensor], comm_stream: "torch.cuda.Stream", group=None):
+    """Same exchange as `allreduce_dbias`, enqueued on `comm_stream` so that it overlaps whatever the caller
+    launches next on the current stream (in training: the rest of the backward pass).  Returns the reduced tensor;
+    it is valid once the consumer stream has waited on `comm_stream`
+    (`torch.cuda.current_stream().wait_stream(comm_stream)`)."""
+    if dbias is None or not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return dbias
+    comm_stream.wait_stream(torch.cuda.current_stream(dbias.device))
+    with torch.cuda.stream(comm_stream):
+        acc = dbias.float()
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
+        out = acc.to(dbias.dtype)
+    dbias.record_stream(comm_stream)
+    return out
