@@ -186,27 +186,31 @@ __global__ void __launch_bounds__(256) rmsnorm_fwd_generic_kernel(const void* __
 // Backward, vectorised: same row ownership as the forward; every thread keeps a private fp32 dW partial
 // in registers, the groups of a block are summed through shared memory, one partial row per block.
 template <int kXDt, int kWDt, int kChunks, int kT>
-__global__ void __launch_bounds__(256) rmsnorm_bwd_vec_kernel(const void* __restrict__ dy, const void* __restrict__ x,
-                                                              const void* __restrict__ w, const float* __restrict__ rstd_in,
-                                                              void* __restrict__ dx, float* __restrict__ dw_partial,
-                                                              int rows, int n, int64_t dys, int64_t xs, int64_t dxs) {
-    extern __shared__ float sdw[];   // [n]
+__global__ void __launch_bounds__(256, 2) rmsnorm_bwd_vec_kernel(const void* __restrict__ dy, const void* __restrict__ x,
+                                                                 const void* __restrict__ w, const float* __restrict__ rstd_in,
+                                                                 void* __restrict__ dx, float* __restrict__ dw_partial,
+                                                                 int rows, int n, int64_t dys, int64_t xs, int64_t dxs) {
+    extern __shared__ float sdyn[];   // [n] dW block partial, then [n] fp32 copy of w
+    float* sdw = sdyn;
+    float* sw = sdyn + n;
     __shared__ float red[8];
     constexpr int kGroups = 256 / kT;
     const int tig = threadIdx.x % kT;
     const int group_global = blockIdx.x * kGroups + threadIdx.x / kT;
     const int groups_total = gridDim.x * kGroups;
-    for (int c = threadIdx.x; c < n; c += blockDim.x) sdw[c] = 0.f;
+    for (int c = threadIdx.x; c < n; c += blockDim.x) {
+        sdw[c] = 0.f;
+        sw[c] = load1<kWDt>(w, c);
+    }
     __syncthreads();
 
-    float wv[kChunks][8], dwv[kChunks][8];
+    // w stays in shared memory (not registers): the kernel then fits 2 blocks per SM, and occupancy -- not
+    // arithmetic -- is what this streaming kernel needs
+    float dwv[kChunks][8];
 #pragma unroll
-    for (int c = 0; c < kChunks; ++c) {
-        const int col = (c * kT + tig) * 8;
+    for (int c = 0; c < kChunks; ++c)
 #pragma unroll
         for (int e = 0; e < 8; ++e) dwv[c][e] = 0.f;
-        if (col < n) load8<kWDt>(w, col, wv[c]);
-    }
     const float inv_n = 1.f / static_cast<float>(n);
     for (int row = group_global; row < rows; row += groups_total) {
         const float rstd = __ldg(rstd_in + row);
@@ -219,10 +223,13 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_vec_kernel(const void* __rest
                 float dyv[8];
                 load8<kXDt>(x, (int64_t)row * xs + col, xh[c]);
                 load8<kXDt>(dy, (int64_t)row * dys + col, dyv);
+                const float4 w0 = *reinterpret_cast<const float4*>(sw + col);
+                const float4 w1 = *reinterpret_cast<const float4*>(sw + col + 4);
+                const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     xh[c][e] *= rstd;
-                    wdy[c][e] = wv[c][e] * dyv[e];
+                    wdy[c][e] = wv[e] * dyv[e];
                     c1 = fmaf(xh[c][e], wdy[c][e], c1);
                     dwv[c][e] = fmaf(dyv[e], xh[c][e], dwv[c][e]);
                 }
@@ -463,7 +470,7 @@ static RmsPlan rms_plan(int n, bool aligned) {
     pl.threads_per_row = n <= 1024 ? 32 : 256;
     const int per = pl.threads_per_row * 8;
     const int need = (n + per - 1) / per;
-    pl.chunks = need <= 1 ? 1 : (need <= 2 ? 2 : 4);
+    pl.chunks = need;          // 1..4
     return pl;
 }
 
@@ -472,12 +479,14 @@ static RmsPlan rms_plan(int n, bool aligned) {
         switch (pl.chunks) {                                \
             case 1: MACRO(1, 32); break;                    \
             case 2: MACRO(2, 32); break;                    \
+            case 3: MACRO(3, 32); break;                    \
             default: MACRO(4, 32); break;                   \
         }                                                   \
     } else {                                                \
         switch (pl.chunks) {                                \
             case 1: MACRO(1, 256); break;                   \
             case 2: MACRO(2, 256); break;                   \
+            case 3: MACRO(3, 256); break;                   \
             default: MACRO(4, 256); break;                  \
         }                                                   \
     }
@@ -514,10 +523,12 @@ cudaError_t launch_rmsnorm_bwd(const void* dy, const void* x, const void* w, con
         if (pl.vec) {
             const int groups = 256 / pl.threads_per_row;
             blocks = std::min((rows + groups - 1) / groups, kRmsnormMaxPartials);
-            const size_t smem = (size_t)n * sizeof(float);
+            const size_t smem = 2 * (size_t)n * sizeof(float);
 #define B200T5_RMS_BWD(CH, T)                                                                                   \
-    B200T5_DISPATCH_DT(x_dtype, XD, B200T5_DISPATCH_DT(w_dtype, WD,                                            \
-        (rmsnorm_bwd_vec_kernel<XD, WD, CH, T><<<blocks, 256, smem, stream>>>(dy, x, w, rstd, dx, dw_partial, rows, n, dys, xs, dxs))))
+    B200T5_DISPATCH_DT(x_dtype, XD, B200T5_DISPATCH_DT(w_dtype, WD, {                                          \
+        if (smem > 48 * 1024)                                                                                   \
+            cudaFuncSetAttribute(rmsnorm_bwd_vec_kernel<XD, WD, CH, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        rmsnorm_bwd_vec_kernel<XD, WD, CH, T><<<blocks, 256, smem, stream>>>(dy, x, w, rstd, dx, dw_partial, rows, n, dys, xs, dxs); }))
             B200T5_RMS_PLAN_DISPATCH(pl, B200T5_RMS_BWD)
 #undef B200T5_RMS_BWD
         } else {
