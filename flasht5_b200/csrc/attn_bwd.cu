@@ -193,16 +193,25 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdKernelParams p) {
                                 bb);
                 }
             }
-        } else if (warp == 5 && lane == 0 && n_iter > 0) {
-            // ---- MMA issuer ----
+        } else if (warp == 5 && n_iter > 0) {
+            // ---- MMA issuer: whole warp runs the loop (warp-uniform descriptor math), one elected lane issues ----
+            const bool leader = elect_one();
             constexpr uint32_t idesc_s = make_idesc(kBf16, 128, 128, false, false);    // S, dP
             constexpr uint32_t idesc_dkv = make_idesc(kBf16, 128, kD, true, true);     // dV, dK
             constexpr uint32_t idesc_dq = make_idesc(kBf16, 128, kD, false, true);     // dQ
             constexpr uint32_t sbo = 8 * C::kRowBytes;
-            const uint32_t k_addr = smem_u32(smem + C::kK);
-            const uint32_t v_addr = smem_u32(smem + C::kV);
-            const uint32_t p_addr = smem_u32(smem + C::kP);
-            const uint32_t ds_addr = smem_u32(smem + C::kDS);
+            constexpr uint32_t hi_op = sdesc_hi(sbo, C::kSwizzle);       // Q, dO, K, V tiles (either major)
+            constexpr uint32_t hi_pds = sdesc_hi(1024, kSwz128);         // P, dS tiles (either major)
+            const uint32_t k_lo = sdesc_lo(smem_u32(smem + C::kK), 16);
+            const uint32_t v_lo = sdesc_lo(smem_u32(smem + C::kV), 16);
+            const uint32_t k_mn_lo = sdesc_lo(smem_u32(smem + C::kK), C::kBoxBytes);
+            const uint32_t q_lo0 = sdesc_lo(smem_u32(smem + C::kQ), 16);
+            const uint32_t do_lo0 = sdesc_lo(smem_u32(smem + C::kDO), 16);
+            const uint32_t q_mn_lo0 = sdesc_lo(smem_u32(smem + C::kQ), C::kBoxBytes);
+            const uint32_t do_mn_lo0 = sdesc_lo(smem_u32(smem + C::kDO), C::kBoxBytes);
+            const uint32_t p_mn_lo = sdesc_lo(smem_u32(smem + C::kP), kHalfBytes);
+            const uint32_t ds_mn_lo = sdesc_lo(smem_u32(smem + C::kDS), kHalfBytes);
+            const uint32_t ds_k_lo = sdesc_lo(smem_u32(smem + C::kDS), 16);
             const uint32_t tm_s = tmem_base + C::kColS;
             const uint32_t tm_dp = tmem_base + C::kColDP;
             const uint32_t tm_dv = tmem_base + C::kColDV;
@@ -210,54 +219,54 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdKernelParams p) {
             const uint32_t tm_dq = tmem_base + C::kColDQ;
 
             auto issue_s_dp = [&](int k) {
-                const int s = k % C::kQStages;
-                const uint32_t q_addr = smem_u32(smem + C::kQ + s * C::kTileBytes);
-                const uint32_t do_addr = smem_u32(smem + C::kDO + s * C::kTileBytes);
+                const uint32_t so = (k % C::kQStages) * (C::kTileBytes >> 4);
+                if (leader) {
 #pragma unroll
-                for (int kk = 0; kk < kD / 16; ++kk) {
-                    const uint32_t off = (kk / 4) * C::kBoxBytes + (kk % 4) * 32;
-                    umma_ss(tm_s, make_sdesc(q_addr + off, 16, sbo, C::kSwizzle),
-                            make_sdesc(k_addr + off, 16, sbo, C::kSwizzle), idesc_s, kk > 0 ? 1u : 0u);
-                }
+                    for (int kk = 0; kk < kD / 16; ++kk) {
+                        const uint32_t off = ((kk / 4) * C::kBoxBytes + (kk % 4) * 32) >> 4;
+                        umma_ss2(tm_s, q_lo0 + so + off, hi_op, k_lo + off, hi_op, idesc_s, kk > 0 ? 1u : 0u);
+                    }
 #pragma unroll
-                for (int kk = 0; kk < kD / 16; ++kk) {
-                    const uint32_t off = (kk / 4) * C::kBoxBytes + (kk % 4) * 32;
-                    umma_ss(tm_dp, make_sdesc(do_addr + off, 16, sbo, C::kSwizzle),
-                            make_sdesc(v_addr + off, 16, sbo, C::kSwizzle), idesc_s, kk > 0 ? 1u : 0u);
+                    for (int kk = 0; kk < kD / 16; ++kk) {
+                        const uint32_t off = ((kk / 4) * C::kBoxBytes + (kk % 4) * 32) >> 4;
+                        umma_ss2(tm_dp, do_lo0 + so + off, hi_op, v_lo + off, hi_op, idesc_s, kk > 0 ? 1u : 0u);
+                    }
+                    umma_commit(sdp_full);
                 }
-                umma_commit(sdp_full);
+                __syncwarp();
             };
             auto issue_grads = [&](int k) {
                 const int s = k % C::kQStages;
-                const uint32_t q_addr = smem_u32(smem + C::kQ + s * C::kTileBytes);
-                const uint32_t do_addr = smem_u32(smem + C::kDO + s * C::kTileBytes);
+                const uint32_t so = s * (C::kTileBytes >> 4);
                 const uint32_t acc = k > 0 ? 1u : 0u;
-                // dV += P^T dO ; dK += dS^T Q      (K dimension = the 128 query rows of this block)
+                if (leader) {
+                    // dV += P^T dO ; dK += dS^T Q      (K dimension = the 128 query rows of this block)
 #pragma unroll
-                for (int kk = 0; kk < kBM / 16; ++kk) {
-                    umma_ss(tm_dv, make_sdesc(p_addr + kk * 2048, kHalfBytes, 1024, kSwz128),
-                            make_sdesc(do_addr + kk * 16 * C::kRowBytes, C::kBoxBytes, sbo, C::kSwizzle), idesc_dkv,
-                            (acc | (kk > 0)) ? 1u : 0u);
-                }
+                    for (int kk = 0; kk < kBM / 16; ++kk)
+                        umma_ss2(tm_dv, p_mn_lo + kk * (2048 >> 4), hi_pds,
+                                 do_mn_lo0 + so + ((kk * 16 * C::kRowBytes) >> 4), hi_op, idesc_dkv,
+                                 (acc | (kk > 0)) ? 1u : 0u);
 #pragma unroll
-                for (int kk = 0; kk < kBM / 16; ++kk) {
-                    umma_ss(tm_dk, make_sdesc(ds_addr + kk * 2048, kHalfBytes, 1024, kSwz128),
-                            make_sdesc(q_addr + kk * 16 * C::kRowBytes, C::kBoxBytes, sbo, C::kSwizzle), idesc_dkv,
-                            (acc | (kk > 0)) ? 1u : 0u);
+                    for (int kk = 0; kk < kBM / 16; ++kk)
+                        umma_ss2(tm_dk, ds_mn_lo + kk * (2048 >> 4), hi_pds,
+                                 q_mn_lo0 + so + ((kk * 16 * C::kRowBytes) >> 4), hi_op, idesc_dkv,
+                                 (acc | (kk > 0)) ? 1u : 0u);
+                    umma_commit(qdo_empty + s);
                 }
-                umma_commit(qdo_empty + s);
+                __syncwarp();
                 // dQ_blk = dS K                    (K dimension = the 128 keys of this CTA)
                 if (k > 0) {
                     mbar_wait(dq_empty, (k - 1) & 1);
                     tc_fence_after();
                 }
+                if (leader) {
 #pragma unroll
-                for (int kk = 0; kk < kBN / 16; ++kk) {
-                    umma_ss(tm_dq, make_sdesc(ds_addr + (kk / 4) * kHalfBytes + (kk % 4) * 32, 16, 1024, kSwz128),
-                            make_sdesc(k_addr + kk * 16 * C::kRowBytes, C::kBoxBytes, sbo, C::kSwizzle), idesc_dq,
-                            kk > 0 ? 1u : 0u);
+                    for (int kk = 0; kk < kBN / 16; ++kk)
+                        umma_ss2(tm_dq, ds_k_lo + (((kk / 4) * kHalfBytes + (kk % 4) * 32) >> 4), hi_pds,
+                                 k_mn_lo + ((kk * 16 * C::kRowBytes) >> 4), hi_op, idesc_dq, kk > 0 ? 1u : 0u);
+                    umma_commit(dq_full);
                 }
-                umma_commit(dq_full);
+                __syncwarp();
             };
 
             mbar_wait(kv_full, 0);
@@ -291,7 +300,8 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdKernelParams p) {
                     issue_grads(k);
                 }
             }
-            umma_commit(acc_full);
+            if (leader) umma_commit(acc_full);
+            __syncwarp();
         }
     } else {
         // =============================== compute warpgroups ===============================
