@@ -316,3 +316,50 @@ def test_full_size_causality():
     o2, L2 = torch.ops.b200t5.attn_bias_fwd(q, k2, v2, bias, True, 1.0)
     assert torch.equal(o[:, :, :700], o2[:, :, :700]) and torch.equal(L[:, :, :700], L2[:, :, :700])
     assert not torch.equal(o[:, :, 700:], o2[:, :, 700:])
+
+
+# ---------------------------------------------------------------------------------------------
+# sizes that exercise the group surfaces and long loops (checked against fp32 torch on the GPU where the
+# CPU oracle would take minutes)
+# ---------------------------------------------------------------------------------------------
+def _torch_fp32_reference(q, k, v, bias, do, causal, scale):
+    qq, kk, vv = (t.float().detach().requires_grad_(True) for t in (q, k, v))
+    bb = bias.float().detach().requires_grad_(True)
+    s = qq @ kk.transpose(2, 3) * scale + bb
+    if causal:
+        M, N = q.shape[2], k.shape[2]
+        mask = torch.arange(M, device=q.device).unsqueeze(-1) + (N - M) >= torch.arange(N, device=q.device)
+        s = s.masked_fill(~mask, float("-inf"))
+    o = torch.softmax(s, -1) @ vv
+    grads = torch.autograd.grad(o, (qq, kk, vv, bb), do.float())
+    return (o.detach(),) + tuple(grads)
+
+
+@pytest.mark.parametrize("B,H,M,N,causal", [(1, 2, 4096, 4096, False), (1, 2, 4096, 4096, True), (2, 2, 1024, 2048, False),
+                                            (1, 1, 640, 8192, False)])
+def test_long_sequences_vs_fp32_torch(B, H, M, N, causal):
+    """32-64 key blocks: the dQ group surface has 4-8 groups; 8-32 query blocks per backward CTA."""
+    g = torch.Generator(device=DEV).manual_seed(M + N)
+    mk = lambda s_: torch.randn(B, s_, H, 64, generator=g, device=DEV).to(torch.bfloat16).permute(0, 2, 1, 3)  # noqa: E731
+    q, k, v, do = mk(M), mk(N), mk(N), mk(M)
+    bias = (0.5 * torch.randn(1, H, M, N, generator=g, device=DEV)).to(torch.bfloat16)
+    scale = 0.125
+    ref = _torch_fp32_reference(q, k, v, bias, do, causal, scale)
+    qd, kd, vd, bd = (t.detach().requires_grad_(True) for t in (q, k, v, bias))
+    from flasht5_b200 import flash_attention_v2_bias
+    o = flash_attention_v2_bias(qd, kd, vd, bd, causal, scale)
+    grads = torch.autograd.grad(o, (qd, kd, vd, bd), do)
+    for name, mine, r in zip(("o", "dq", "dk", "dv", "dbias"), (o,) + tuple(grads), ref):
+        mx, rf = orc.error_metrics(mine, r)
+        assert rf <= TOL[torch.bfloat16][name], (name, mx, rf)
+
+
+def test_many_batches_group_surface_cap():
+    """B = 160 > 8 * 16: the batch-group surface is capped at 16 groups of 10 batches each."""
+    B, H, S, D = 160, 1, 128, 32
+    q, k, v, bias, do = _make(B, H, S, S, D, torch.bfloat16, "1H", "bshd", 9)
+    o, L, dq, dk, dv, db = orc.attn_fwd_bwd(q.float(), k.float(), v.float(), bias.float(), do.float(), True, 0.3)
+    got = _run(q, k, v, bias, do, True, 0.3)
+    for name, r in (("o", o), ("dq", dq), ("dk", dk), ("dv", dv), ("dbias", db)):
+        mx, rf = orc.error_metrics(got[name], r)
+        assert rf <= TOL[torch.bfloat16][name], (name, mx, rf)
