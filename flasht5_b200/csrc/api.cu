@@ -321,7 +321,9 @@ extern "C" int b200t5_attn_bwd(const b200t5_attn_params* p) {
     void* dq_ws = ws + w.dq_off;
     void* ds_ws = ws + w.ds_off;
 
-    cudaError_t e = launch_attn_bwd_preprocess(p->o, p->o_strides, p->dout, p->do_strides, delta, dq_ws, w.dq_groups, p->B, p->H, p->M, p->D, bf16, stream);
+    // delta, zero-fill of the dQ group surface and (when dS is reduce-added) of the dS group surface: one launch
+    cudaError_t e = launch_attn_bwd_preprocess(p->o, p->o_strides, p->dout, p->do_strides, delta, dq_ws, w.dq_groups, p->B, p->H, p->M, p->D, bf16,
+                                               w.ds_use_reduce ? ds_ws : nullptr, w.ds_use_reduce ? (w.ds_bytes + 15) / 16 * 16 : 0, stream);
     if (e != cudaSuccess) return fail_cuda(e, "attn_bwd_preprocess launch");
 
     const CUtensorMapDataType dt = bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
@@ -347,10 +349,6 @@ extern "C" int b200t5_attn_bwd(const b200t5_attn_params* p) {
     if (mode != 0) {
         // dS tiles always go to the (B, H, M, n_pad) 16-bit workspace through TMA stores
         if ((rc = make_map_4d(&kp.map_ds, ds_ws, 2, dt, p->N, p->M, p->H, w.ds_groups, w.n_pad, (int64_t)p->M * w.n_pad, (int64_t)p->H * p->M * w.n_pad, 64, 128, "dS workspace"))) return rc;
-        if (w.ds_use_reduce) {
-            e = cudaMemsetAsync(ds_ws, 0, w.ds_bytes, stream);
-            if (e != cudaSuccess) return fail_cuda(e, "dS workspace memset");
-        }
     }
     kp.ds_groups = w.ds_groups > 0 ? w.ds_groups : 1;
     kp.ds_use_reduce = w.ds_use_reduce;
@@ -370,14 +368,10 @@ extern "C" int b200t5_attn_bwd(const b200t5_attn_params* p) {
     }
     if (e != cudaSuccess) return fail_cuda(e, "attn_bwd launch");
 
-    e = launch_attn_bwd_dq_convert(dq_ws, w.dq_groups, p->dq, p->dq_strides, p->B, p->H, p->M, p->D, p->sm_scale, bf16, stream);
-    if (e != cudaSuccess) return fail_cuda(e, "attn_bwd_dq_convert launch");
-
-    if (mode != 0) {
-        // the reduce kernel sees the group dim as its "batch": (groups, H, M, n_pad) -> dbias
-        e = launch_dbias_reduce(ds_ws, w.n_pad, p->dbias, p->dbias_strides, w.ds_groups, p->H, p->M, p->N, p->bias_B == 1, p->bias_H == 1, p->causal != 0, bf16, stream);
-        if (e != cudaSuccess) return fail_cuda(e, "dbias_reduce launch");
-    }
+    e = launch_attn_bwd_finalize(dq_ws, w.dq_groups, p->dq, p->dq_strides, p->B, p->H, p->M, p->N, p->D, p->sm_scale, bf16,
+                                 ds_ws, w.n_pad, mode != 0 ? p->dbias : nullptr, p->dbias_strides, w.ds_groups > 0 ? w.ds_groups : 1,
+                                 p->bias_B == 1, p->bias_H == 1, p->causal != 0, stream);
+    if (e != cudaSuccess) return fail_cuda(e, "attn_bwd_finalize launch");
     return 0;
 }
 

@@ -525,7 +525,8 @@ template <int kD, bool kBf16>
 __global__ void attn_bwd_preprocess_kernel(const uint8_t* __restrict__ o, int64_t o_sb, int64_t o_sh, int64_t o_sm,
                                            const uint8_t* __restrict__ dout, int64_t do_sb, int64_t do_sh,
                                            int64_t do_sm, float* __restrict__ delta, uint4* __restrict__ dq_ws,
-                                           int dq_groups, int B, int H, int M) {
+                                           int dq_groups, int B, int H, int M, uint4* __restrict__ zero_ptr,
+                                           int64_t zero_chunks) {
     constexpr int kTpr = kD / 8;                              // threads per row, 8 elements (16 B) each
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t row = gid / kTpr;
@@ -553,6 +554,8 @@ __global__ void attn_bwd_preprocess_kernel(const uint8_t* __restrict__ o, int64_
 #pragma unroll
     for (int off = kTpr / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
     if (row < rows && part == 0) delta[row] = acc;
+    // zero-fill of the dS batch-group surface (replaces a separate memset node)
+    for (int64_t i = gid; i < zero_chunks; i += (int64_t)gridDim.x * blockDim.x) zero_ptr[i] = make_uint4(0, 0, 0, 0);
 }
 
 template <int kD, bool kBf16>
@@ -670,6 +673,92 @@ __global__ void dbias_reduce_vec8_kernel(const uint4* __restrict__ ws, int pitch
     }
 }
 
+// dq convert + dBias reduce in ONE launch (they are independent; one grid, block-index split): blocks
+// [0, cvt_blocks) run the dQ conversion, the rest run the vectorised dBias reduction.
+template <int kD, bool kBf16>
+__global__ void attn_bwd_finalize_kernel(const uint4* __restrict__ dq_ws, int dq_groups, uint8_t* __restrict__ dq,
+                                         int64_t sb, int64_t sh, int64_t sm, int B, int H, int M, float scale,
+                                         int cvt_blocks, const uint4* __restrict__ ds_ws, int pitch8,
+                                         uint4* __restrict__ dbias, int G, int N, int reduce_b, int reduce_h,
+                                         int causal) {
+    if (static_cast<int>(blockIdx.x) < cvt_blocks) {
+        constexpr int kTpr = kD / 8;
+        const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        const int64_t row = gid / kTpr;
+        const int part = static_cast<int>(gid % kTpr);
+        const int64_t rows = (int64_t)B * H * M;
+        if (row >= rows) return;
+        const int m = static_cast<int>(row % M);
+        const int64_t bh = row / M;
+        const int hh = static_cast<int>(bh % H);
+        const int64_t bb = bh / H;
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+        for (int g = 0; g < dq_groups; ++g) {
+            const uint4 u = __ldg(dq_ws + (g * rows + row) * kTpr + part);
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = unpack2<kBf16>(w[e]);
+                acc[2 * e] += f.x;
+                acc[2 * e + 1] += f.y;
+            }
+        }
+        uint4 out;
+        out.x = pack2<kBf16>(acc[0] * scale, acc[1] * scale);
+        out.y = pack2<kBf16>(acc[2] * scale, acc[3] * scale);
+        out.z = pack2<kBf16>(acc[4] * scale, acc[5] * scale);
+        out.w = pack2<kBf16>(acc[6] * scale, acc[7] * scale);
+        *reinterpret_cast<uint4*>(dq + 2 * (bb * sb + hh * sh + m * sm + part * 8)) = out;
+        return;
+    }
+    // ---- dBias: sum of the G group slices (and of a broadcast head dim), fp32, one rounding ----
+    const int n8 = N / 8;
+    const int64_t mn8 = (int64_t)M * n8;
+    const int64_t mp8 = (int64_t)M * pitch8;
+    const int ob_n = reduce_b ? 1 : G;
+    const int oh_n = reduce_h ? 1 : H;
+    const int64_t total = (int64_t)ob_n * oh_n * mn8;
+    const int64_t nthreads = (int64_t)(gridDim.x - cvt_blocks) * blockDim.x;
+    for (int64_t idx = (int64_t)(blockIdx.x - cvt_blocks) * blockDim.x + threadIdx.x; idx < total; idx += nthreads) {
+        const int c8 = static_cast<int>(idx % n8);
+        int64_t t = idx / n8;
+        const int m = static_cast<int>(t % M);
+        t /= M;
+        const int oh = static_cast<int>(t % oh_n);
+        const int ob = static_cast<int>(t / oh_n);
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+        const int vis = causal ? (m + (N - M) + 1 - c8 * 8) : 8;
+        if (vis > 0) {
+            const int b0 = reduce_b ? 0 : ob, b1 = reduce_b ? G : ob + 1;
+            const int h0 = reduce_h ? 0 : oh, h1 = reduce_h ? H : oh + 1;
+            for (int bb = b0; bb < b1; ++bb)
+                for (int hh = h0; hh < h1; ++hh) {
+                    const uint4 u = __ldg(ds_ws + ((int64_t)bb * H + hh) * mp8 + (int64_t)m * pitch8 + c8);
+                    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 f = unpack2<kBf16>(w[e]);
+                        acc[2 * e] += f.x;
+                        acc[2 * e + 1] += f.y;
+                    }
+                }
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                if (e >= vis) acc[e] = 0.f;
+        }
+        uint4 o;
+        o.x = pack2<kBf16>(acc[0], acc[1]);
+        o.y = pack2<kBf16>(acc[2], acc[3]);
+        o.z = pack2<kBf16>(acc[4], acc[5]);
+        o.w = pack2<kBf16>(acc[6], acc[7]);
+        dbias[idx] = o;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------
@@ -717,14 +806,15 @@ cudaError_t launch_attn_bwd(const AttnBwdKernelParams& kp, int D, bool bf16, int
 
 cudaError_t launch_attn_bwd_preprocess(const void* o, const int64_t* os, const void* dout, const int64_t* ds,
                                        float* delta, void* dq_ws, int dq_groups, int B, int H, int M, int D,
-                                       bool bf16, cudaStream_t stream) {
+                                       bool bf16, void* zero_ptr, size_t zero_bytes, cudaStream_t stream) {
     const int64_t threads = (int64_t)B * H * M * (D / 8);
     const int block = 256;
     const int grid = static_cast<int>((threads + block - 1) / block);
 #define B200T5_PRE(DD, BF)                                                                                         \
     attn_bwd_preprocess_kernel<DD, BF><<<grid, block, 0, stream>>>(                                                \
         static_cast<const uint8_t*>(o), os[0], os[1], os[2], static_cast<const uint8_t*>(dout), ds[0], ds[1],     \
-        ds[2], delta, static_cast<uint4*>(dq_ws), dq_groups, B, H, M)
+        ds[2], delta, static_cast<uint4*>(dq_ws), dq_groups, B, H, M, static_cast<uint4*>(zero_ptr),            \
+        static_cast<int64_t>(zero_bytes / 16))
     switch (D) {
         case 16: if (bf16) B200T5_PRE(16, true); else B200T5_PRE(16, false); break;
         case 32: if (bf16) B200T5_PRE(32, true); else B200T5_PRE(32, false); break;
@@ -789,6 +879,49 @@ cudaError_t launch_dbias_reduce(const void* ds_ws, int ws_pitch, void* dbias, co
                                                                    static_cast<uint16_t*>(dbias), s[0], s[1], s[2],
                                                                    s[3], B, H, M, N, reduce_b, reduce_h, causal ? 1 : 0);
     }
+    count_launch();
+    return cudaGetLastError();
+}
+
+// dQ conversion and (when there is a bias) the dBias reduction.  One fused launch when dBias is contiguous and
+// 16-byte addressable, two launches otherwise.
+cudaError_t launch_attn_bwd_finalize(const void* dq_ws, int dq_groups, void* dq, const int64_t* dqs, int B, int H, int M,
+                                     int N, int D, float sm_scale, bool bf16, const void* ds_ws, int ws_pitch, void* dbias,
+                                     const int64_t* dbs, int G, int reduce_b, int reduce_h, bool causal,
+                                     cudaStream_t stream) {
+    bool fused = dbias != nullptr;
+    if (fused) {
+        const int ob = reduce_b ? 1 : G, oh = reduce_h ? 1 : H;
+        const bool contiguous = dbs[3] == 1 && dbs[2] == N && (oh == 1 || dbs[1] == (int64_t)M * N) &&
+                                (ob == 1 || dbs[0] == (int64_t)oh * M * N);
+        fused = contiguous && (N % 8 == 0) && ((reinterpret_cast<uintptr_t>(dbias) & 15) == 0) &&
+                ((reinterpret_cast<uintptr_t>(ds_ws) & 15) == 0);
+    }
+    if (!fused) {
+        cudaError_t e = launch_attn_bwd_dq_convert(dq_ws, dq_groups, dq, dqs, B, H, M, D, sm_scale, bf16, stream);
+        if (e != cudaSuccess || dbias == nullptr) return e;
+        return launch_dbias_reduce(ds_ws, ws_pitch, dbias, dbs, G, H, M, N, reduce_b, reduce_h, causal, bf16, stream);
+    }
+    const int block = 256;
+    const int64_t cvt_threads = (int64_t)B * H * M * (D / 8);
+    const int cvt_blocks = static_cast<int>((cvt_threads + block - 1) / block);
+    const int ob = reduce_b ? 1 : G, oh = reduce_h ? 1 : H;
+    const int64_t red_total = (int64_t)ob * oh * M * (N / 8);
+    const int red_blocks = static_cast<int>(std::min<int64_t>((red_total + block - 1) / block, 148 * 16));
+    const int grid = cvt_blocks + red_blocks;
+#define B200T5_FIN(DD, BF)                                                                                          \
+    attn_bwd_finalize_kernel<DD, BF><<<grid, block, 0, stream>>>(                                                   \
+        static_cast<const uint4*>(dq_ws), dq_groups, static_cast<uint8_t*>(dq), dqs[0], dqs[1], dqs[2], B, H, M,    \
+        sm_scale, cvt_blocks, static_cast<const uint4*>(ds_ws), ws_pitch / 8, static_cast<uint4*>(dbias), G, N,     \
+        reduce_b, reduce_h, causal ? 1 : 0)
+    switch (D) {
+        case 16: if (bf16) B200T5_FIN(16, true); else B200T5_FIN(16, false); break;
+        case 32: if (bf16) B200T5_FIN(32, true); else B200T5_FIN(32, false); break;
+        case 64: if (bf16) B200T5_FIN(64, true); else B200T5_FIN(64, false); break;
+        case 128: if (bf16) B200T5_FIN(128, true); else B200T5_FIN(128, false); break;
+        default: return cudaErrorInvalidValue;
+    }
+#undef B200T5_FIN
     count_launch();
     return cudaGetLastError();
 }

@@ -60,9 +60,16 @@ cudaError_t launch_attn_bwd_v2(const AttnBwdKernelParams& kp, int D, bool bf16, 
                                cudaStream_t stream);
 
 // delta[b,h,m] = sum_d O*dO  (fp32); also zero-fills the 16-bit dQ group surface (dq_groups, B, H, M, D).
+// `zero_ptr` / `zero_bytes` (multiple of 16, may be 0): an extra surface to zero-fill in the same launch.
 cudaError_t launch_attn_bwd_preprocess(const void* o, const int64_t* o_strides, const void* dout,
                                        const int64_t* do_strides, float* delta, void* dq_ws, int dq_groups, int B,
-                                       int H, int M, int D, bool bf16, cudaStream_t stream);
+                                       int H, int M, int D, bool bf16, void* zero_ptr, size_t zero_bytes,
+                                       cudaStream_t stream);
+// dq convert + dBias reduce (one fused launch when possible); dbias may be NULL
+cudaError_t launch_attn_bwd_finalize(const void* dq_ws, int dq_groups, void* dq, const int64_t* dq_strides, int B, int H,
+                                     int M, int N, int D, float sm_scale, bool bf16, const void* ds_ws, int ws_pitch,
+                                     void* dbias, const int64_t* dbias_strides, int G, int reduce_b, int reduce_h,
+                                     bool causal, cudaStream_t stream);
 // dq[b,h,m,:] = 16bit(sm_scale * sum_g dq_ws[g,b,h,m,:])
 cudaError_t launch_attn_bwd_dq_convert(const void* dq_ws, int dq_groups, void* dq, const int64_t* dq_strides, int B,
                                        int H, int M, int D, float sm_scale, bool bf16, cudaStream_t stream);
