@@ -10,10 +10,12 @@ class names, same argument meaning.  No Triton, no multi-backend dispatch, no CP
 from .flash_attention_v2_bias import FlashAttentionAdditiveBias, flash_attention_v2_bias
 from .rms_norm import Fast_RMS_Layernorm, fast_rms_layernorm
 from .cross_entropy_loss import CrossEntropyLoss, cross_entropy_loss
+from .positional_encoding import RelativePositionalEncoding
 
 __all__ = [
     "flash_attention_v2_bias", "FlashAttentionAdditiveBias",
     "fast_rms_layernorm", "Fast_RMS_Layernorm",
     "cross_entropy_loss", "CrossEntropyLoss",
+    "RelativePositionalEncoding",
 ]
 __version__ = "0.1.0"

@@ -55,6 +55,8 @@ SYMBOLS = {
     "b200t5_ce_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _f, _f, _f, _i64, _i32, _i32, _vp]),
     "b200t5_ce_bwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _f, _f, _f, _i64, _i32, _i32,
                              _vp]),
+    "b200t5_t5_bias_fwd": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "b200t5_t5_bias_bwd": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "b200t5_abi_version": (_i32, []),
     "b200t5_last_error": (C.c_char_p, []),
     "b200t5_launch_count": (C.c_uint64, []),

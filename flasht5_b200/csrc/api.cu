@@ -458,6 +458,45 @@ extern "C" int b200t5_ce_bwd(const void* logits, const int64_t* labels, const fl
 }
 
 // ------------------------------------------------------------------------------------------
+// T5 relative-position bias producer
+// ------------------------------------------------------------------------------------------
+static int check_t5_args(const void* a, const void* b, const int32_t* lut, int lut_len, int H, int M, int N, int nb) {
+    if (!a || !b || !lut) return fail(B200T5_ERR_INVALID, "table/dbias, bias/dtable and lut must be non-NULL");
+    if (H < 1 || M < 1 || N < 1 || lut_len < 1) return fail(B200T5_ERR_INVALID, "H, M, N, lut_len must be >= 1");
+    if (nb < 1 || nb > 256) return fail(B200T5_ERR_UNSUPPORTED, "num_buckets %d not in [1, 256]", nb);
+    return 0;
+}
+
+extern "C" int b200t5_t5_bias_fwd(const void* table, const int32_t* lut, int32_t lut_zero, int32_t lut_len,
+                                  const int32_t* ctx_pos, const int32_t* mem_pos, void* bias, int32_t H, int32_t M,
+                                  int32_t N, int32_t num_buckets, int table_dtype, int bias_dtype, int device,
+                                  void* stream) {
+    int rc;
+    if ((rc = check_t5_args(table, bias, lut, lut_len, H, M, N, num_buckets))) return rc;
+    if ((rc = check_dtype3(table_dtype, "table")) || (rc = check_dtype3(bias_dtype, "bias"))) return rc;
+    if ((rc = require_sm100(device))) return rc;
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return fail_cuda(guard.err, "cudaSetDevice");
+    cudaError_t e = launch_t5_bias_fwd(table, lut, lut_zero, lut_len, ctx_pos, mem_pos, bias, H, M, N, num_buckets, table_dtype, bias_dtype, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail_cuda(e, "t5_bias_fwd launch");
+    return 0;
+}
+
+extern "C" int b200t5_t5_bias_bwd(const void* dbias, const int32_t* lut, int32_t lut_zero, int32_t lut_len,
+                                  const int32_t* ctx_pos, const int32_t* mem_pos, float* dtable, int32_t H, int32_t M,
+                                  int32_t N, int32_t num_buckets, int dbias_dtype, int device, void* stream) {
+    int rc;
+    if ((rc = check_t5_args(dbias, dtable, lut, lut_len, H, M, N, num_buckets))) return rc;
+    if ((rc = check_dtype3(dbias_dtype, "dbias"))) return rc;
+    if ((rc = require_sm100(device))) return rc;
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return fail_cuda(guard.err, "cudaSetDevice");
+    cudaError_t e = launch_t5_bias_bwd(dbias, lut, lut_zero, lut_len, ctx_pos, mem_pos, dtable, H, M, N, num_buckets, dbias_dtype, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail_cuda(e, "t5_bias_bwd launch");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // library state
 // ------------------------------------------------------------------------------------------
 extern "C" int b200t5_abi_version(void) { return B200T5_ABI_VERSION; }

@@ -92,6 +92,16 @@ cudaError_t launch_ce_bwd(const void* logits, const int64_t* labels, const float
                           int64_t dlogits_row_stride, float smoothing, float logit_scale, float lse_square_scale,
                           int64_t ignore_index, int dtype, cudaStream_t stream);
 
+// T5 relative-position bias producer (t5_bias.cu).  lut[rel + lut_zero] = bucket, rel = mem_pos[n] - ctx_pos[m]
+// (positions default to 0..M-1 / 0..N-1 when the pointers are NULL).  table: (num_buckets, H); bias: (1, H, M, N)
+// contiguous; dtable: (num_buckets, H) fp32, zeroed by the launcher.
+cudaError_t launch_t5_bias_fwd(const void* table, const int32_t* lut, int lut_zero, int lut_len, const int32_t* ctx_pos,
+                               const int32_t* mem_pos, void* bias, int H, int M, int N, int num_buckets, int table_dtype,
+                               int bias_dtype, cudaStream_t stream);
+cudaError_t launch_t5_bias_bwd(const void* dbias, const int32_t* lut, int lut_zero, int lut_len, const int32_t* ctx_pos,
+                               const int32_t* mem_pos, float* dtable, int H, int M, int N, int num_buckets, int dbias_dtype,
+                               cudaStream_t stream);
+
 // Launch counter (every kernel launched by this library bumps it; read through the C ABI).
 void count_launch(int n = 1);
 

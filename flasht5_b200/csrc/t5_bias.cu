@@ -1,0 +1,184 @@
+// T5 relative-position bias producer for sm_100a: the step immediately upstream of the attention operator
+// (SURVEY.md section 8, row f1).
+//
+// Replaces /root/reference/src/utils/positional_encoding.py:73-102 (`compute_bias`: bucket -> nn.Embedding gather
+// -> permute -> (1, H, M, N)) and the backward of that gather (scatter-add of dBias into the (num_buckets, H) table).
+// The relative-position -> bucket map is passed in as a lookup table over the relative distance (built by the
+// caller with the reference's own formula, :25-71, so the buckets are bit-identical); these kernels do the two
+// HBM-bound parts: the dense gather (writes H*M*N elements once, directly in the attention dtype -- no fp32
+// (1,H,M,N) intermediate) and the segmented sum.
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200t5 {
+
+namespace {
+
+template <int kDt>
+__device__ __forceinline__ float ld_elem(const void* p, int64_t i) {
+    if constexpr (kDt == 2) return __ldg(static_cast<const float*>(p) + i);
+    else return to_float16bit<kDt == 1>(__ldg(static_cast<const uint16_t*>(p) + i));
+}
+
+constexpr int kMaxBuckets = 256;
+
+// grid = (ceil(M / kRows), H); block = 256 threads; each thread produces 8 consecutive key positions of one row
+constexpr int kRowsPerBlock = 8;
+
+template <int kTabDt, int kOutDt>
+__global__ void __launch_bounds__(256) t5_bias_fwd_kernel(const void* __restrict__ table, const int32_t* __restrict__ lut,
+                                                          int lut_zero, int lut_len, const int32_t* __restrict__ ctx_pos,
+                                                          const int32_t* __restrict__ mem_pos, void* __restrict__ bias,
+                                                          int H, int M, int N, int num_buckets) {
+    __shared__ float s_tab[kMaxBuckets];
+    const int h = blockIdx.y;
+    for (int i = threadIdx.x; i < num_buckets; i += blockDim.x) s_tab[i] = ld_elem<kTabDt>(table, (int64_t)i * H + h);
+    __syncthreads();
+    const int m0 = blockIdx.x * kRowsPerBlock;
+    for (int mi = 0; mi < kRowsPerBlock; ++mi) {
+        const int m = m0 + mi;
+        if (m >= M) break;
+        const int cp = ctx_pos ? __ldg(ctx_pos + m) : m;
+        const int64_t row = ((int64_t)h * M + m) * N;
+        for (int n0 = threadIdx.x * 8; n0 < N; n0 += blockDim.x * 8) {
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int n = n0 + e;
+                float val = 0.f;
+                if (n < N) {
+                    int idx = (mem_pos ? __ldg(mem_pos + n) : n) - cp + lut_zero;
+                    idx = idx < 0 ? 0 : (idx >= lut_len ? lut_len - 1 : idx);
+                    val = s_tab[__ldg(lut + idx)];
+                }
+                v[e] = val;
+            }
+            if constexpr (kOutDt == 2) {
+                float* o = static_cast<float*>(bias) + row + n0;
+                if (n0 + 8 <= N && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                    reinterpret_cast<float4*>(o)[0] = make_float4(v[0], v[1], v[2], v[3]);
+                    reinterpret_cast<float4*>(o)[1] = make_float4(v[4], v[5], v[6], v[7]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        if (n0 + e < N) o[e] = v[e];
+                }
+            } else {
+                uint16_t* o = static_cast<uint16_t*>(bias) + row + n0;
+                if (n0 + 8 <= N && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                    uint4 u;
+                    u.x = pack2<kOutDt == 1>(v[0], v[1]);
+                    u.y = pack2<kOutDt == 1>(v[2], v[3]);
+                    u.z = pack2<kOutDt == 1>(v[4], v[5]);
+                    u.w = pack2<kOutDt == 1>(v[6], v[7]);
+                    *reinterpret_cast<uint4*>(o) = u;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        if (n0 + e < N) o[e] = static_cast<uint16_t>(pack2<kOutDt == 1>(v[e], 0.f) & 0xFFFFu);
+                }
+            }
+        }
+    }
+}
+
+// dTable[bucket, h] += sum of dBias[h, m, n] over the (m, n) that map to the bucket.  Per-warp shared-memory
+// histograms (runs of equal buckets are summed in registers first: neighbouring keys mostly share a bucket),
+// then one global atomicAdd per (block, bucket).  dtable (num_buckets, H) fp32 must be zero on entry.
+template <int kInDt>
+__global__ void __launch_bounds__(256) t5_bias_bwd_kernel(const void* __restrict__ dbias, const int32_t* __restrict__ lut,
+                                                          int lut_zero, int lut_len, const int32_t* __restrict__ ctx_pos,
+                                                          const int32_t* __restrict__ mem_pos, float* __restrict__ dtable,
+                                                          int H, int M, int N, int num_buckets, int rows_per_block) {
+    extern __shared__ float s_hist[];                 // [8 warps][num_buckets]
+    const int warp = threadIdx.x >> 5;
+    float* my = s_hist + warp * num_buckets;
+    for (int i = threadIdx.x; i < 8 * num_buckets; i += blockDim.x) s_hist[i] = 0.f;
+    __syncthreads();
+    const int h = blockIdx.y;
+    const int m0 = blockIdx.x * rows_per_block;
+    for (int mi = 0; mi < rows_per_block; ++mi) {
+        const int m = m0 + mi;
+        if (m >= M) break;
+        const int cp = ctx_pos ? __ldg(ctx_pos + m) : m;
+        const int64_t row = ((int64_t)h * M + m) * N;
+        for (int n0 = threadIdx.x * 8; n0 < N; n0 += blockDim.x * 8) {
+            float run = 0.f;
+            int run_b = -1;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int n = n0 + e;
+                if (n < N) {
+                    int idx = (mem_pos ? __ldg(mem_pos + n) : n) - cp + lut_zero;
+                    idx = idx < 0 ? 0 : (idx >= lut_len ? lut_len - 1 : idx);
+                    const int bkt = __ldg(lut + idx);
+                    const float g = ld_elem<kInDt>(dbias, row + n);
+                    if (bkt != run_b) {
+                        if (run_b >= 0) atomicAdd(my + run_b, run);
+                        run_b = bkt;
+                        run = 0.f;
+                    }
+                    run += g;
+                }
+            }
+            if (run_b >= 0) atomicAdd(my + run_b, run);
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < num_buckets; b += blockDim.x) {
+        float acc = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) acc += s_hist[w * num_buckets + b];
+        if (acc != 0.f) atomicAdd(dtable + (int64_t)b * H + h, acc);
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_t5_bias_fwd(const void* table, const int32_t* lut, int lut_zero, int lut_len, const int32_t* ctx_pos,
+                               const int32_t* mem_pos, void* bias, int H, int M, int N, int num_buckets, int table_dtype,
+                               int bias_dtype, cudaStream_t stream) {
+    if (num_buckets > kMaxBuckets) return cudaErrorInvalidValue;
+    const dim3 grid((M + kRowsPerBlock - 1) / kRowsPerBlock, H);
+#define B200T5_T5F(TD, OD)                                                                                          \
+    t5_bias_fwd_kernel<TD, OD><<<grid, 256, 0, stream>>>(table, lut, lut_zero, lut_len, ctx_pos, mem_pos, bias, H, M, N, \
+                                                         num_buckets)
+    switch (table_dtype * 3 + bias_dtype) {
+        case 0: B200T5_T5F(0, 0); break;
+        case 1: B200T5_T5F(0, 1); break;
+        case 2: B200T5_T5F(0, 2); break;
+        case 3: B200T5_T5F(1, 0); break;
+        case 4: B200T5_T5F(1, 1); break;
+        case 5: B200T5_T5F(1, 2); break;
+        case 6: B200T5_T5F(2, 0); break;
+        case 7: B200T5_T5F(2, 1); break;
+        default: B200T5_T5F(2, 2); break;
+    }
+#undef B200T5_T5F
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_t5_bias_bwd(const void* dbias, const int32_t* lut, int lut_zero, int lut_len, const int32_t* ctx_pos,
+                               const int32_t* mem_pos, float* dtable, int H, int M, int N, int num_buckets, int dbias_dtype,
+                               cudaStream_t stream) {
+    if (num_buckets > kMaxBuckets) return cudaErrorInvalidValue;
+    cudaError_t e = cudaMemsetAsync(dtable, 0, (size_t)num_buckets * H * sizeof(float), stream);
+    if (e != cudaSuccess) return e;
+    // enough blocks to fill the chip a few times over, few enough that the global atomics stay negligible
+    int rows_per_block = std::max(1, (M * H + 148 * 8 - 1) / (148 * 8));
+    rows_per_block = std::min(rows_per_block, 64);
+    const dim3 grid((M + rows_per_block - 1) / rows_per_block, H);
+    const size_t smem = 8 * (size_t)num_buckets * sizeof(float);
+    switch (dbias_dtype) {
+        case 0: t5_bias_bwd_kernel<0><<<grid, 256, smem, stream>>>(dbias, lut, lut_zero, lut_len, ctx_pos, mem_pos, dtable, H, M, N, num_buckets, rows_per_block); break;
+        case 1: t5_bias_bwd_kernel<1><<<grid, 256, smem, stream>>>(dbias, lut, lut_zero, lut_len, ctx_pos, mem_pos, dtable, H, M, N, num_buckets, rows_per_block); break;
+        default: t5_bias_bwd_kernel<2><<<grid, 256, smem, stream>>>(dbias, lut, lut_zero, lut_len, ctx_pos, mem_pos, dtable, H, M, N, num_buckets, rows_per_block); break;
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace b200t5

@@ -125,6 +125,24 @@ B200T5_API int b200t5_ce_bwd(const void* logits, const int64_t* labels, const fl
                   int64_t ignore_index, int dtype, int device, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * T5 relative-position bias producer (the step that builds the attention operator's `bias` input).
+ * Replaces RelativePositionalEncoding.compute_bias, src/utils/positional_encoding.py:73-102 (bucket -> embedding
+ * gather -> (1,H,M,N)) and the scatter-add backward of that gather.
+ * table: (num_buckets, H) row-major, dtype table_dtype.  lut: int32[lut_len], lut[rel + lut_zero] = bucket of the
+ * relative position rel = mem_pos[n] - ctx_pos[m] (out-of-range indices are clamped); the caller builds it with the
+ * reference formula (:25-71).  ctx_pos: int32[M] or NULL (= 0..M-1); mem_pos: int32[N] or NULL (= 0..N-1).
+ * bias / dbias: (1, H, M, N) contiguous, dtype bias_dtype / dbias_dtype.  dtable: (num_buckets, H) fp32, overwritten.
+ * num_buckets <= 256.  All dtypes in {F16, BF16, F32}.
+ * ---------------------------------------------------------------------------------------------- */
+B200T5_API int b200t5_t5_bias_fwd(const void* table, const int32_t* lut, int32_t lut_zero, int32_t lut_len,
+                                  const int32_t* ctx_pos, const int32_t* mem_pos, void* bias, int32_t H, int32_t M,
+                                  int32_t N, int32_t num_buckets, int table_dtype, int bias_dtype, int device,
+                                  void* stream);
+B200T5_API int b200t5_t5_bias_bwd(const void* dbias, const int32_t* lut, int32_t lut_zero, int32_t lut_len,
+                                  const int32_t* ctx_pos, const int32_t* mem_pos, float* dtable, int32_t H, int32_t M,
+                                  int32_t N, int32_t num_buckets, int dbias_dtype, int device, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Library state
  * ---------------------------------------------------------------------------------------------- */
 B200T5_API int b200t5_abi_version(void);

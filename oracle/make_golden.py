@@ -185,8 +185,29 @@ def gen_ce():
         print(f"ce_{rows}x{V}: ok")
 
 
+def gen_t5_bias():
+    """compute_bias + the embedding backward of the REFERENCE module (CPU), for both bucket kinds and M != N."""
+    rng = np.random.default_rng(21)
+    for name, (H, M, N, bidir, nb, maxd) in {"bidir_40x56": (3, 40, 56, True, 32, 128), "unidir_64x64": (4, 64, 64, False, 32, 128),
+                                             "bidir_300x300_nb16": (2, 300, 300, True, 16, 64)}.items():
+        pe = RelativePositionalEncoding(nb, maxd, H, max(M, N), bidirectional=bidir)
+        table = torch.from_numpy(rng.standard_normal((nb, H)).astype(np.float32))
+        with torch.no_grad():
+            pe.relative_attention_bias.weight.copy_(table)
+        bias = pe.compute_bias(M, N)
+        dbias = torch.from_numpy(rng.standard_normal((1, H, M, N)).astype(np.float32))
+        (dtable,) = torch.autograd.grad(bias, pe.relative_attention_bias.weight, dbias)
+        mine = attn_bias_ref.t5_bias(table, M, N, bidirectional=bidir, num_buckets=nb, max_distance=maxd)
+        assert torch.equal(mine, bias.detach()), name
+        np.savez_compressed(os.path.join(GOLD, f"t5bias_{name}.npz"), table=table.numpy(), bias=bias.detach().numpy(),
+                            dbias=dbias.numpy(), dtable=dtable.numpy(), M=np.array(M), N=np.array(N), bidirectional=np.array(bidir),
+                            num_buckets=np.array(nb), max_distance=np.array(maxd))
+        print(f"t5bias_{name}: ok")
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
+    gen_t5_bias()
     gen_buckets()
     gen_attn()
     gen_rmsnorm()

@@ -70,6 +70,21 @@ def main():
               (rows, V, t_f, bf / t_f / 1e6, bf / t_f / 1e6 / peak, t_b, bb / t_b / 1e6, bb / t_b / 1e6 / peak, t_bi))
         del logits
         torch.cuda.empty_cache()
+    # T5 bias producer: table (32, H) -> bias (1, H, S, S) bf16 and back
+    from flasht5_b200.positional_encoding import RelativePositionalEncoding
+    for H, S in ((8, 1024), (12, 1024), (16, 4096)):
+        pe = RelativePositionalEncoding(32, 128, H, S, bidirectional=True).to(dev)
+        bias = pe.compute_bias(S, S, dtype=torch.bfloat16)
+        gb = torch.randn_like(bias)
+        lut = pe._bucket_lut(-(S - 1), S - 1, dev)
+        w = pe.relative_attention_bias.weight.detach()
+        t_f = timeit(lambda: torch.ops.b200t5.t5_bias_fwd(w, lut, S - 1, None, None, S, S, torch.bfloat16), flush)
+        t_b = timeit(lambda: torch.ops.b200t5.t5_bias_bwd(gb, lut, S - 1, None, None, 32), flush)
+        nbytes = H * S * S * 2
+        res.append({"op": "t5_bias", "H": H, "S": S, "fwd_ms": t_f, "bwd_ms": t_b, "fwd_gbs": nbytes / t_f / 1e6,
+                    "bwd_gbs": nbytes / t_b / 1e6, "fwd_frac": nbytes / t_f / 1e6 / peak, "bwd_frac": nbytes / t_b / 1e6 / peak})
+        print("t5bias  H=%2d S=%4d     fwd %.4f ms %6.0f GB/s (%.2f)   bwd %.4f ms %6.0f GB/s (%.2f)" %
+              (H, S, t_f, nbytes / t_f / 1e6, nbytes / t_f / 1e6 / peak, t_b, nbytes / t_b / 1e6, nbytes / t_b / 1e6 / peak))
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     json.dump({"hbm_peak_gbs": peak, "results": res}, open(a.out, "w"), indent=1)
 
