@@ -135,12 +135,162 @@ __global__ void __launch_bounds__(256) t5_bias_bwd_kernel(const void* __restrict
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Toeplitz fast paths (default positions 0..M-1 / 0..N-1): bias[h, m, n] depends on n - m only.
+// One block = one head x kTRows consecutive rows; the diagonal values those rows touch (N + kTRows - 1 of them)
+// are staged once in shared memory, so the per-element work is one conflict-free shared load (forward) or one
+// coalesced global load (backward) -- no per-element bucket lookup.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kTRows = 32;
+
+template <int kTabDt, int kOutDt>
+__global__ void __launch_bounds__(256) t5_bias_fwd_toeplitz_kernel(const void* __restrict__ table,
+                                                                   const int32_t* __restrict__ lut, int lut_zero,
+                                                                   int lut_len, void* __restrict__ bias, int H, int M,
+                                                                   int N, int num_buckets) {
+    extern __shared__ float s_dyn[];              // [num_buckets] table column, then [N + kTRows - 1] diagonal values
+    float* s_tab = s_dyn;
+    float* s_vec = s_dyn + kMaxBuckets;
+    const int h = blockIdx.y;
+    const int m0 = blockIdx.x * kTRows;
+    for (int i = threadIdx.x; i < num_buckets; i += blockDim.x) s_tab[i] = ld_elem<kTabDt>(table, (int64_t)i * H + h);
+    __syncthreads();
+    // s_vec[j] = value of relative position  j - (m0 + kTRows - 1)
+    const int seg = N + kTRows - 1;
+    for (int j = threadIdx.x; j < seg; j += blockDim.x) {
+        int idx = j - (m0 + kTRows - 1) + lut_zero;
+        idx = idx < 0 ? 0 : (idx >= lut_len ? lut_len - 1 : idx);
+        s_vec[j] = s_tab[__ldg(lut + idx)];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int mi = warp; mi < kTRows; mi += 8) {
+        const int m = m0 + mi;
+        if (m >= M) break;
+        const float* src = s_vec + (kTRows - 1 - mi);          // src[n] = bias[h, m, n]
+        const int64_t row = ((int64_t)h * M + m) * N;
+        if constexpr (kOutDt == 2) {
+            float* o = static_cast<float*>(bias) + row;
+            for (int n = lane; n < N; n += 32) o[n] = src[n];
+        } else {
+            uint16_t* o = static_cast<uint16_t*>(bias) + row;
+            if ((row & 1) == 0) {                               // 4-byte aligned row: packed pairs, 128 B per warp store
+                for (int n = 2 * lane; n < N; n += 64) {
+                    if (n + 1 < N) *reinterpret_cast<uint32_t*>(o + n) = pack2<kOutDt == 1>(src[n], src[n + 1]);
+                    else o[n] = static_cast<uint16_t>(pack2<kOutDt == 1>(src[n], 0.f) & 0xFFFFu);
+                }
+            } else {
+                for (int n = lane; n < N; n += 32) o[n] = static_cast<uint16_t>(pack2<kOutDt == 1>(src[n], 0.f) & 0xFFFFu);
+            }
+        }
+    }
+}
+
+// Backward: one block = one head x 32 rows; each warp takes 32x32 tiles.  Row r of a tile is rotated by r lanes
+// with a shuffle, after which lane l holds an element of diagonal l (no wrap) or l - 32 (wrapped): two running
+// sums per lane collect the tile's 63 diagonals with one shuffle + one add per row and NO atomics; the tile then
+// adds 2 values per lane to the block's shared diagonal segment, which is folded into buckets at the end.
+template <int kInDt>
+__global__ void __launch_bounds__(256) t5_bias_bwd_toeplitz_kernel(const void* __restrict__ dbias,
+                                                                   const int32_t* __restrict__ lut, int lut_zero,
+                                                                   int lut_len, float* __restrict__ dtable, int H, int M,
+                                                                   int N, int num_buckets) {
+    extern __shared__ float s_dyn[];              // [N + 63] diagonal sums of this row group, then [8 warps][num_buckets]
+    const int seg = N + 2 * kTRows - 1;
+    float* s_hist = s_dyn + seg;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h = blockIdx.y;
+    const int m0 = blockIdx.x * kTRows;
+    for (int i = threadIdx.x; i < seg + 8 * num_buckets; i += blockDim.x) s_dyn[i] = 0.f;
+    __syncthreads();
+    // s_dyn[j] <-> relative position j - (kTRows - 1) - m0 ... i.e. element (m0 + r, n) lands at j = n - r + (kTRows - 1)
+    const int ntiles = (N + 31) / 32;
+    for (int t = warp; t < ntiles; t += 8) {
+        const int n = t * 32 + lane;
+        float acc_lo = 0.f, acc_hi = 0.f;          // diagonals (lane) and (lane - 32) of this tile
+        float v[kTRows];
+#pragma unroll
+        for (int r = 0; r < kTRows; ++r) {         // all 32 row loads in flight before the first shuffle
+            const int m = m0 + r;
+            v[r] = (m < M && n < N) ? ld_elem<kInDt>(dbias, ((int64_t)h * M + m) * N + n) : 0.f;
+        }
+#pragma unroll
+        for (int r = 0; r < kTRows; ++r) {
+            // lane l receives column (l + r) % 32 of row r: its diagonal is (l + r) % 32 - r = l  or  l - 32
+            const float w = __shfl_sync(0xffffffffu, v[r], (lane + r) & 31);
+            if (lane + r < 32) acc_lo += w; else acc_hi += w;
+        }
+        // tile-local diagonal c - r = lane (acc_lo) / lane - 32 (acc_hi); global j = t*32 + diag + (kTRows - 1)
+        atomicAdd(s_dyn + t * 32 + lane + (kTRows - 1), acc_lo);
+        if (lane > 0) atomicAdd(s_dyn + t * 32 + lane - 32 + (kTRows - 1), acc_hi);
+    }
+    __syncthreads();
+    // fold the diagonal sums into buckets.  Neighbouring diagonals mostly share a bucket and shared-memory float
+    // atomics on ONE address serialise (CAS loop), so each warp first sums its lanes per distinct bucket with
+    // shuffles and only the group leader touches the warp's private histogram row -- no atomics.
+    float* my_hist = s_hist + warp * num_buckets;
+    for (int j0 = warp * 32; j0 < seg; j0 += 256) {
+        const int j = j0 + lane;
+        float acc = 0.f;
+        int bkt = -1;
+        if (j < seg) {
+            acc = s_dyn[j];
+            int idx = j - (kTRows - 1) - m0 + lut_zero;
+            idx = idx < 0 ? 0 : (idx >= lut_len ? lut_len - 1 : idx);
+            bkt = __ldg(lut + idx);
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, bkt >= 0);
+        while (todo) {
+            const int leader = __ffs(todo) - 1;
+            const int b = __shfl_sync(0xffffffffu, bkt, leader);
+            const unsigned grp = __ballot_sync(0xffffffffu, bkt == b);
+            float v = bkt == b ? acc : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == leader) my_hist[b] += v;
+            todo &= ~grp;
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < num_buckets; b += blockDim.x) {
+        float acc = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) acc += s_hist[w * num_buckets + b];
+        if (acc != 0.f) atomicAdd(dtable + (int64_t)b * H + h, acc);
+    }
+}
+
 }  // namespace
 
 cudaError_t launch_t5_bias_fwd(const void* table, const int32_t* lut, int lut_zero, int lut_len, const int32_t* ctx_pos,
                                const int32_t* mem_pos, void* bias, int H, int M, int N, int num_buckets, int table_dtype,
                                int bias_dtype, cudaStream_t stream) {
     if (num_buckets > kMaxBuckets) return cudaErrorInvalidValue;
+    if (ctx_pos == nullptr && mem_pos == nullptr && (size_t)(kMaxBuckets + N + kTRows) * 4 <= 200 * 1024) {
+        const dim3 tgrid((M + kTRows - 1) / kTRows, H);
+        const size_t smem = (size_t)(kMaxBuckets + N + kTRows - 1) * sizeof(float);
+#define B200T5_T5FT(TD, OD)                                                                                         \
+    {                                                                                                               \
+        if (smem > 48 * 1024)                                                                                       \
+            cudaFuncSetAttribute(t5_bias_fwd_toeplitz_kernel<TD, OD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        t5_bias_fwd_toeplitz_kernel<TD, OD><<<tgrid, 256, smem, stream>>>(table, lut, lut_zero, lut_len, bias, H, M, N, num_buckets); \
+    }
+        switch (table_dtype * 3 + bias_dtype) {
+            case 0: B200T5_T5FT(0, 0); break;
+            case 1: B200T5_T5FT(0, 1); break;
+            case 2: B200T5_T5FT(0, 2); break;
+            case 3: B200T5_T5FT(1, 0); break;
+            case 4: B200T5_T5FT(1, 1); break;
+            case 5: B200T5_T5FT(1, 2); break;
+            case 6: B200T5_T5FT(2, 0); break;
+            case 7: B200T5_T5FT(2, 1); break;
+            default: B200T5_T5FT(2, 2); break;
+        }
+#undef B200T5_T5FT
+        count_launch();
+        return cudaGetLastError();
+    }
     const dim3 grid((M + kRowsPerBlock - 1) / kRowsPerBlock, H);
 #define B200T5_T5F(TD, OD)                                                                                          \
     t5_bias_fwd_kernel<TD, OD><<<grid, 256, 0, stream>>>(table, lut, lut_zero, lut_len, ctx_pos, mem_pos, bias, H, M, N, \
@@ -167,6 +317,26 @@ cudaError_t launch_t5_bias_bwd(const void* dbias, const int32_t* lut, int lut_ze
     if (num_buckets > kMaxBuckets) return cudaErrorInvalidValue;
     cudaError_t e = cudaMemsetAsync(dtable, 0, (size_t)num_buckets * H * sizeof(float), stream);
     if (e != cudaSuccess) return e;
+    {
+        const size_t smem = ((size_t)N + 2 * kTRows - 1 + 8 * (size_t)num_buckets) * sizeof(float);
+        if (ctx_pos == nullptr && mem_pos == nullptr && smem <= 200 * 1024) {
+            const dim3 tgrid((M + kTRows - 1) / kTRows, H);
+#define B200T5_T5BT(DT)                                                                                             \
+    {                                                                                                               \
+        if (smem > 48 * 1024)                                                                                       \
+            cudaFuncSetAttribute(t5_bias_bwd_toeplitz_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        t5_bias_bwd_toeplitz_kernel<DT><<<tgrid, 256, smem, stream>>>(dbias, lut, lut_zero, lut_len, dtable, H, M, N, num_buckets); \
+    }
+            switch (dbias_dtype) {
+                case 0: B200T5_T5BT(0); break;
+                case 1: B200T5_T5BT(1); break;
+                default: B200T5_T5BT(2); break;
+            }
+#undef B200T5_T5BT
+            count_launch();
+            return cudaGetLastError();
+        }
+    }
     // enough blocks to fill the chip a few times over, few enough that the global atomics stay negligible
     int rows_per_block = std::max(1, (M * H + 148 * 8 - 1) / (148 * 8));
     rows_per_block = std::min(rows_per_block, 64);
