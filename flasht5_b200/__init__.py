@@ -3,6 +3,7 @@ the RMSNorm and cross-entropy ops) as hand-written sm_100a CUDA behind a C ABI, 
 reference's own Python operator surface on top.
 
     from flasht5_b200 import flash_attention_v2_bias, fast_rms_layernorm, cross_entropy_loss
+    from flasht5_b200 import RelativePositionalEncoding, flash_attention_v2_rpe   # bias producer / in-kernel bias
 
 The layout follows the reference's src/model/ops/: one module per operator, same function and
 class names, same argument meaning.  No Triton, no multi-backend dispatch, no CPU fallback.
@@ -11,11 +12,13 @@ from .flash_attention_v2_bias import FlashAttentionAdditiveBias, flash_attention
 from .rms_norm import Fast_RMS_Layernorm, fast_rms_layernorm
 from .cross_entropy_loss import CrossEntropyLoss, cross_entropy_loss
 from .positional_encoding import RelativePositionalEncoding
+from .flash_attention_rpe import FlashAttentionRPE, flash_attention_v2_rpe
 
 __all__ = [
     "flash_attention_v2_bias", "FlashAttentionAdditiveBias",
     "fast_rms_layernorm", "Fast_RMS_Layernorm",
     "cross_entropy_loss", "CrossEntropyLoss",
     "RelativePositionalEncoding",
+    "flash_attention_v2_rpe", "FlashAttentionRPE",
 ]
 __version__ = "0.1.0"

@@ -42,6 +42,17 @@ class AttnParams(C.Structure):
     ]
 
 
+class RpeParams(C.Structure):
+    """Mirror of `b200t5_rpe_params` (include/b200t5.h)."""
+    _fields_ = [
+        ("table", C.c_void_p), ("table_stride_b", C.c_int64), ("table_stride_h", C.c_int64),
+        ("table_dtype", C.c_int32), ("num_buckets", C.c_int32),
+        ("lut", C.c_void_p), ("lut_zero", C.c_int32), ("lut_len", C.c_int32),
+        ("const_lo", C.c_int32), ("const_hi", C.c_int32),
+        ("band", C.c_void_p), ("dtable", C.c_void_p),
+    ]
+
+
 # every symbol include/b200t5.h declares: name -> (restype, argtypes)
 _i64, _i32, _f, _vp, _sz = C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_size_t
 SYMBOLS = {
@@ -57,6 +68,11 @@ SYMBOLS = {
                              _vp]),
     "b200t5_t5_bias_fwd": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "b200t5_t5_bias_bwd": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "b200t5_rpe_band_len": (_i32, [_i32, _i32]),
+    "b200t5_rpe_band": (_i32, [C.POINTER(RpeParams), _i32, _i32, _i32, _vp]),
+    "b200t5_attn_rpe_fwd": (_i32, [C.POINTER(AttnParams), C.POINTER(RpeParams)]),
+    "b200t5_attn_rpe_bwd_workspace_bytes": (_sz, [C.POINTER(AttnParams), C.POINTER(RpeParams)]),
+    "b200t5_attn_rpe_bwd": (_i32, [C.POINTER(AttnParams), C.POINTER(RpeParams)]),
     "b200t5_abi_version": (_i32, []),
     "b200t5_last_error": (C.c_char_p, []),
     "b200t5_launch_count": (C.c_uint64, []),
@@ -64,7 +80,7 @@ SYMBOLS = {
     "b200t5_profile_enable": (_i32, [_i32]),
     "b200t5_profile_collect": (_i32, [C.POINTER(C.c_int), C.POINTER(C.c_float), _i32]),
 }
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _lib = None
 _lock = threading.Lock()

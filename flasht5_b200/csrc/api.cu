@@ -204,14 +204,49 @@ static int bias_mode_of(const b200t5_attn_params* p) {
 }
 
 static int round_up8(int x) { return (x + 7) / 8 * 8; }
+static int check_dtype3(int dt, const char* what) {
+    if (dt == B200T5_F16 || dt == B200T5_BF16 || dt == B200T5_F32) return 0;
+    return fail(B200T5_ERR_UNSUPPORTED, "%s dtype %d not in {fp16, bf16, fp32}", what, dt);
+}
+
+// ---- in-kernel relative-position bias (bias mode 3) ----
+static int rpe_band_len(int const_lo, int const_hi) { return const_hi - const_lo + 2 * kRpeBandPad + 1; }
+
+static int validate_rpe(const b200t5_rpe_params* r, bool need_table, bool need_bwd) {
+    if (!r) return fail(B200T5_ERR_INVALID, "rpe params is NULL");
+    if (r->const_lo >= r->const_hi) return fail(B200T5_ERR_INVALID, "rpe: const_lo (%d) must be < const_hi (%d)", r->const_lo, r->const_hi);
+    if ((int64_t)r->const_hi - r->const_lo > kRpeMaxBandLen) return fail(B200T5_ERR_UNSUPPORTED, "rpe: %lld distinct relative positions between const_lo and const_hi; at most %d fit the kernels (use the dense-bias path)", (long long)r->const_hi - r->const_lo, kRpeMaxBandLen - 2 * kRpeBandPad - 1);
+    if (rpe_band_len(r->const_lo, r->const_hi) > kRpeMaxBandLen) return fail(B200T5_ERR_UNSUPPORTED, "rpe: band of %d relative positions exceeds %d (use the dense-bias path)", rpe_band_len(r->const_lo, r->const_hi), kRpeMaxBandLen);
+    if (!r->band) return fail(B200T5_ERR_INVALID, "rpe: band buffer is NULL");
+    if (reinterpret_cast<uintptr_t>(r->band) % 4 != 0) return fail(B200T5_ERR_INVALID, "rpe: band buffer is not 4-byte aligned");
+    if (need_table || need_bwd) {
+        if (!r->lut || r->lut_len < 1) return fail(B200T5_ERR_INVALID, "rpe: lut is NULL or empty");
+        if (r->num_buckets < 1 || r->num_buckets > 256) return fail(B200T5_ERR_UNSUPPORTED, "rpe: num_buckets %d not in [1, 256]", r->num_buckets);
+    }
+    if (need_table && !r->table) return fail(B200T5_ERR_INVALID, "rpe: table is NULL");
+    if (need_bwd && !r->dtable) return fail(B200T5_ERR_INVALID, "rpe: dtable is NULL");
+    return 0;
+}
+
+static void fill_rpe_band(RpeBand* rb, const b200t5_rpe_params* r) {
+    rb->band = r->band;
+    rb->const_lo = r->const_lo;
+    rb->const_hi = r->const_hi;
+    rb->band_lo = r->const_lo - kRpeBandPad;
+    rb->band_len = rpe_band_len(r->const_lo, r->const_hi);
+}
 
 }  // namespace b200t5
 
 using namespace b200t5;
 
-extern "C" int b200t5_attn_fwd(const b200t5_attn_params* p) {
+static int attn_fwd_impl(const b200t5_attn_params* p, const b200t5_rpe_params* rpe) {
     int rc = validate_common(p);
     if (rc) return rc;
+    if (rpe) {
+        if (p->bias) return fail(B200T5_ERR_INVALID, "the relative-position entry points take bias == NULL");
+        if ((rc = validate_rpe(rpe, false, false))) return rc;
+    }
     if ((rc = require_sm100(p->device))) return rc;
     DeviceGuard guard(p->device);
     if (guard.err != cudaSuccess) return fail_cuda(guard.err, "cudaSetDevice");
@@ -223,7 +258,7 @@ extern "C" int b200t5_attn_fwd(const b200t5_attn_params* p) {
     if ((rc = make_map_4d(&kp.map_q, p->q, 2, dt, p->D, p->M, p->H, p->B, p->q_strides[2], p->q_strides[1], p->q_strides[0], boxd, 128, "q"))) return rc;
     if ((rc = make_map_4d(&kp.map_k, p->k, 2, dt, p->D, p->N, p->H, p->B, p->k_strides[2], p->k_strides[1], p->k_strides[0], boxd, 128, "k"))) return rc;
     if ((rc = make_map_4d(&kp.map_v, p->v, 2, dt, p->D, p->N, p->H, p->B, p->v_strides[2], p->v_strides[1], p->v_strides[0], boxd, 128, "v"))) return rc;
-    const int mode = bias_mode_of(p);
+    const int mode = rpe ? 3 : bias_mode_of(p);
     if (mode == 1) {
         if ((rc = make_map_4d(&kp.map_bias, p->bias, 2, dt, p->N, p->M, p->bias_H, p->bias_B, p->bias_strides[2], p->bias_strides[1], p->bias_strides[0], 64, 128, "bias"))) return rc;
     } else if (mode == 2) {
@@ -232,6 +267,8 @@ extern "C" int b200t5_attn_fwd(const b200t5_attn_params* p) {
         kp.bias_sh = p->bias_strides[1];
         kp.bias_sm = p->bias_strides[2];
         kp.bias_sn = p->bias_strides[3];
+    } else if (mode == 3) {
+        fill_rpe_band(&kp.rpe, rpe);
     }
     kp.o = p->o;
     kp.o_sb = p->o_strides[0];
@@ -252,12 +289,20 @@ extern "C" int b200t5_attn_fwd(const b200t5_attn_params* p) {
     return 0;
 }
 
+extern "C" int b200t5_attn_fwd(const b200t5_attn_params* p) { return attn_fwd_impl(p, nullptr); }
+extern "C" int b200t5_attn_rpe_fwd(const b200t5_attn_params* p, const b200t5_rpe_params* r) {
+    if (!r) return fail(B200T5_ERR_INVALID, "rpe params is NULL");
+    return attn_fwd_impl(p, r);
+}
+
 namespace {
 struct BwdWorkspace {
-    size_t delta_off, dq_off, ds_off, ds_bytes, total;
+    size_t delta_off, dq_off, ds_off, ds_bytes, dbias_off, total;
     int n_pad, ds_groups, ds_use_reduce, dq_groups;
 };
-BwdWorkspace bwd_workspace_layout(const b200t5_attn_params* p) {
+// has_rpe: the bias is the in-kernel relative-position bias, i.e. a (1, H, M, N) bias whose dense gradient is only
+// an intermediate (kept in the workspace and folded into the (num_buckets, H) table gradient).
+BwdWorkspace bwd_workspace_layout(const b200t5_attn_params* p, bool has_rpe = false) {
     BwdWorkspace w;
     auto align = [](size_t x) { return (x + 255) / 256 * 256; };
     const size_t rows = (size_t)p->B * p->H * p->M;
@@ -277,8 +322,8 @@ BwdWorkspace bwd_workspace_layout(const b200t5_attn_params* p) {
     w.ds_groups = 0;
     w.ds_use_reduce = 0;
     size_t ds_bytes = 0;
-    if (p->bias) {
-        if (p->bias_B == 1 && p->B > 1) {
+    if (p->bias || has_rpe) {
+        if ((has_rpe || p->bias_B == 1) && p->B > 1) {
             int g = (p->B + 7) / 8;
             if (g > 16) g = 16;
             w.ds_groups = g;
@@ -289,7 +334,8 @@ BwdWorkspace bwd_workspace_layout(const b200t5_attn_params* p) {
         ds_bytes = (size_t)w.ds_groups * p->H * p->M * (size_t)w.n_pad * 2;
     }
     w.ds_bytes = ds_bytes;
-    w.total = w.ds_off + align(ds_bytes);
+    w.dbias_off = w.ds_off + align(ds_bytes);
+    w.total = w.dbias_off + (has_rpe ? align((size_t)p->H * p->M * (size_t)p->N * 2) : 0);
     return w;
 }
 }  // namespace
@@ -299,15 +345,26 @@ extern "C" size_t b200t5_attn_bwd_workspace_bytes(const b200t5_attn_params* p) {
     return bwd_workspace_layout(p).total;
 }
 
-extern "C" int b200t5_attn_bwd(const b200t5_attn_params* p) {
+extern "C" size_t b200t5_attn_rpe_bwd_workspace_bytes(const b200t5_attn_params* p, const b200t5_rpe_params* r) {
+    if (!p || !r || p->B < 1 || p->H < 1 || p->M < 1 || p->N < 1 || p->D < 1) return 0;
+    return bwd_workspace_layout(p, true).total;
+}
+
+static int attn_bwd_impl(const b200t5_attn_params* p, const b200t5_rpe_params* rpe) {
     int rc = validate_common(p);
     if (rc) return rc;
     if (!p->dout || !p->dq || !p->dk || !p->dv) return fail(B200T5_ERR_INVALID, "dout, dq, dk, dv must be non-NULL");
     if ((p->bias != nullptr) != (p->dbias != nullptr)) return fail(B200T5_ERR_INVALID, "dbias must be given exactly when bias is");
+    if (rpe) {
+        if (p->bias) return fail(B200T5_ERR_INVALID, "the relative-position entry points take bias == NULL and dbias == NULL");
+        if ((rc = validate_rpe(rpe, false, true))) return rc;
+        if (rpe->lut_zero < p->M - 1 || rpe->lut_len - 1 - rpe->lut_zero < p->N - 1)
+            return fail(B200T5_ERR_INVALID, "rpe: lut (zero %d, len %d) does not cover relative positions %d..%d", rpe->lut_zero, rpe->lut_len, -(p->M - 1), p->N - 1);
+    }
     if (!strides_tma_ok(p->dout, p->do_strides, p->B, p->H) || !strides_tma_ok(p->dq, p->dq_strides, p->B, p->H) ||
         !strides_tma_ok(p->dk, p->dk_strides, p->B, p->H) || !strides_tma_ok(p->dv, p->dv_strides, p->B, p->H))
         return fail(B200T5_ERR_INVALID, "dout, dq, dk, dv need unit last stride, 16-byte aligned base and other strides that are multiples of 8 elements");
-    const BwdWorkspace w = bwd_workspace_layout(p);
+    const BwdWorkspace w = bwd_workspace_layout(p, rpe != nullptr);
     if (!p->workspace || p->workspace_bytes < w.total) return fail(B200T5_ERR_WORKSPACE, "workspace of %zu bytes needed, %zu given", w.total, p->workspace ? p->workspace_bytes : (size_t)0);
     if (reinterpret_cast<uintptr_t>(p->workspace) % 256 != 0) return fail(B200T5_ERR_WORKSPACE, "workspace must be 256-byte aligned");
     if ((rc = require_sm100(p->device))) return rc;
@@ -336,7 +393,8 @@ extern "C" int b200t5_attn_bwd(const b200t5_attn_params* p) {
     if ((rc = make_map_4d(&kp.map_do, p->dout, 2, dt, p->D, p->M, p->H, p->B, p->do_strides[2], p->do_strides[1], p->do_strides[0], boxd, 128, "dout"))) return rc;
     if ((rc = make_map_4d(&kp.map_dq, dq_ws, 2, dt, p->D, p->M, p->H, (uint64_t)w.dq_groups * p->B, p->D, (int64_t)p->M * p->D, (int64_t)p->H * p->M * p->D, boxd, 128, "dq group surface", true))) return rc;
     kp.dq_groups = w.dq_groups;
-    const int mode = bias_mode_of(p);
+    const int mode = rpe ? 3 : bias_mode_of(p);
+    if (mode == 3) fill_rpe_band(&kp.rpe, rpe);
     if (mode == 1) {
         if ((rc = make_map_4d(&kp.map_bias, p->bias, 2, dt, p->N, p->M, p->bias_H, p->bias_B, p->bias_strides[2], p->bias_strides[1], p->bias_strides[0], 64, 128, "bias"))) return rc;
     } else if (mode == 2) {
@@ -360,7 +418,7 @@ extern "C" int b200t5_attn_bwd(const b200t5_attn_params* p) {
     kp.num_m_blocks = (p->M + 127) / 128;
     kp.num_n_blocks = (p->N + 127) / 128;
     kp.bias_b_bcast = p->bias ? (p->bias_B == 1) : 1;
-    kp.bias_h_bcast = p->bias ? (p->bias_H == 1) : 1;
+    kp.bias_h_bcast = p->bias ? (p->bias_H == 1) : (rpe ? 0 : 1);
     kp.sm_scale = p->sm_scale;
     {
         ProfScope prof(B200T5_KERNEL_ATTN_BWD, stream);
@@ -368,6 +426,20 @@ extern "C" int b200t5_attn_bwd(const b200t5_attn_params* p) {
     }
     if (e != cudaSuccess) return fail_cuda(e, "attn_bwd launch");
 
+    if (rpe) {
+        // dense (1, H, M, N) gradient into the workspace (sum over the batch groups), then the producer's segmented
+        // sum folds it into the (num_buckets, H) table gradient
+        void* dbias_ws = ws + w.dbias_off;
+        const int64_t dbias_strides[4] = {(int64_t)p->H * p->M * p->N, (int64_t)p->M * p->N, p->N, 1};
+        e = launch_attn_bwd_finalize(dq_ws, w.dq_groups, p->dq, p->dq_strides, p->B, p->H, p->M, p->N, p->D, p->sm_scale, bf16,
+                                     ds_ws, w.n_pad, dbias_ws, dbias_strides, w.ds_groups > 0 ? w.ds_groups : 1,
+                                     1, 0, p->causal != 0, stream);
+        if (e != cudaSuccess) return fail_cuda(e, "attn_bwd_finalize launch");
+        e = launch_t5_bias_bwd(dbias_ws, rpe->lut, rpe->lut_zero, rpe->lut_len, nullptr, nullptr, rpe->dtable, p->H, p->M, p->N,
+                               rpe->num_buckets, p->dtype, stream);
+        if (e != cudaSuccess) return fail_cuda(e, "t5_bias_bwd launch");
+        return 0;
+    }
     e = launch_attn_bwd_finalize(dq_ws, w.dq_groups, p->dq, p->dq_strides, p->B, p->H, p->M, p->N, p->D, p->sm_scale, bf16,
                                  ds_ws, w.n_pad, mode != 0 ? p->dbias : nullptr, p->dbias_strides, w.ds_groups > 0 ? w.ds_groups : 1,
                                  p->bias_B == 1, p->bias_H == 1, p->causal != 0, stream);
@@ -375,13 +447,37 @@ extern "C" int b200t5_attn_bwd(const b200t5_attn_params* p) {
     return 0;
 }
 
+extern "C" int b200t5_attn_bwd(const b200t5_attn_params* p) { return attn_bwd_impl(p, nullptr); }
+extern "C" int b200t5_attn_rpe_bwd(const b200t5_attn_params* p, const b200t5_rpe_params* r) {
+    if (!r) return fail(B200T5_ERR_INVALID, "rpe params is NULL");
+    return attn_bwd_impl(p, r);
+}
+
+extern "C" int b200t5_rpe_band_len(int32_t const_lo, int32_t const_hi) {
+    if (const_lo >= const_hi) return 0;
+    const int64_t n = (int64_t)const_hi - const_lo + 2 * kRpeBandPad + 1;
+    return n > 0x7FFFFFFF ? 0 : (int)n;
+}
+
+extern "C" int b200t5_rpe_band(const b200t5_rpe_params* r, int32_t H, int io_dtype, int device, void* stream) {
+    int rc = validate_rpe(r, true, false);
+    if (rc) return rc;
+    if (H < 1) return fail(B200T5_ERR_INVALID, "H must be >= 1");
+    if (!(io_dtype == B200T5_F16 || io_dtype == B200T5_BF16)) return fail(B200T5_ERR_UNSUPPORTED, "io dtype %d is not fp16/bf16", io_dtype);
+    if ((rc = check_dtype3(r->table_dtype, "table"))) return rc;
+    if ((rc = require_sm100(device))) return rc;
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return fail_cuda(guard.err, "cudaSetDevice");
+    cudaError_t e = launch_rpe_band(r->table, r->table_stride_b, r->table_stride_h, r->table_dtype, r->lut, r->lut_zero, r->lut_len,
+                                    r->band, H, r->const_lo - kRpeBandPad, rpe_band_len(r->const_lo, r->const_hi), io_dtype,
+                                    static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail_cuda(e, "rpe_band launch");
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // RMSNorm / cross-entropy
 // ------------------------------------------------------------------------------------------
-static int check_dtype3(int dt, const char* what) {
-    if (dt == B200T5_F16 || dt == B200T5_BF16 || dt == B200T5_F32) return 0;
-    return fail(B200T5_ERR_UNSUPPORTED, "%s dtype %d not in {fp16, bf16, fp32}", what, dt);
-}
 
 extern "C" int b200t5_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int64_t rows, int64_t n,
                                   int64_t x_row_stride, int64_t y_row_stride, float eps, int x_dtype, int w_dtype,

@@ -320,6 +320,16 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdKernelParams p) {
         const int bb = p.bias_b_bcast ? 0 : b;
         const float scale_log2 = p.sm_scale * kLog2e;
 
+        // bias mode 3 (T5 relative-position bias computed in the kernel, see attn_fwd.cu): the per-head band of
+        // bias values replaces the dense bias halves in shared memory
+        const float* band = reinterpret_cast<const float*>(smem + C::kBias);
+        if (kBiasMode == 3) {
+            float* dst = reinterpret_cast<float*>(smem + C::kBias);
+            const float* src = p.rpe.band + (int64_t)h * p.rpe.band_len;
+            for (int i = ctid; i < p.rpe.band_len; i += 256) dst[i] = __ldg(src + i);
+            named_bar_sync(4, 256);
+        }
+
         for (int k = 0; k < n_iter; ++k) {
             const int mrow0 = (i_start + k) * kBM;
             const int grow = mrow0 + r;
@@ -337,6 +347,16 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdKernelParams p) {
                 lim = cl < lim ? cl : lim;
             }
             const bool need_mask = (col0 + kBN > p.N) || (kCausal && (col0 + kBN - 1 > mrow0 + pseq));
+            // bias mode 3: relative positions n - m of this tile are [col0 - mrow0 - 127, col0 - mrow0 + 127]
+            bool rpe_const = false;
+            float rpe_cval = 0.f;
+            if (kBiasMode == 3) {
+                const int rel_min = col0 - mrow0 - (kBM - 1);
+                const int rel_max = col0 - mrow0 + (kBN - 1);
+                rpe_const = rel_max <= p.rpe.const_lo || rel_min >= p.rpe.const_hi;
+                if (rpe_const)
+                    rpe_cval = band[(rel_max <= p.rpe.const_lo ? p.rpe.const_lo : p.rpe.const_hi) - p.rpe.band_lo];
+            }
 
             mbar_wait(sdp_full, k & 1);
             tc_fence_after();
@@ -373,6 +393,15 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdKernelParams p) {
                         for (int e = 0; e < 8; ++e) {
                             const int c = col0 + wg * 64 + ch * 32 + c8 * 8 + e;
                             bv[e] = (row_ok && c < p.N) ? to_float16bit<kBf16>(__ldg(bp + (int64_t)c * p.bias_sn)) : 0.f;
+                        }
+                    } else if (kBiasMode == 3) {
+                        if (rpe_const) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) bv[e] = rpe_cval;
+                        } else {
+                            const float* bp = band + (col0 + wg * 64 + ch * 32 + c8 * 8 - grow - p.rpe.band_lo);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) bv[e] = bp[e];
                         }
                     } else {
 #pragma unroll
@@ -782,8 +811,15 @@ static cudaError_t launch_bwd_d(const AttnBwdKernelParams& kp, int bias_mode, bo
         case 2: return launch_bwd_inst<kD, kBf16, 1, false>(kp, stream);
         case 3: return launch_bwd_inst<kD, kBf16, 1, true>(kp, stream);
         case 4: return launch_bwd_inst<kD, kBf16, 2, false>(kp, stream);
-        default: return launch_bwd_inst<kD, kBf16, 2, true>(kp, stream);
+        case 5: return launch_bwd_inst<kD, kBf16, 2, true>(kp, stream);
+        default: break;
     }
+    // bias mode 3 is only instantiated where this kernel is the production path (D = 128)
+    if constexpr (kD == 128) {
+        if (bias_mode == 3)
+            return causal ? launch_bwd_inst<kD, kBf16, 3, true>(kp, stream) : launch_bwd_inst<kD, kBf16, 3, false>(kp, stream);
+    }
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_attn_bwd(const AttnBwdKernelParams& kp, int D, bool bf16, int bias_mode, bool causal,

@@ -23,6 +23,9 @@
 //   warp 5 : tcgen05.mma issuer                                 warps 0-3, 8-11 : compute (64 columns each)
 //
 // TMEM columns: S [0,128) | dP [128,256) | dV [256,256+D) | dK [256+D,256+2D) | dQ [256+2D,256+3D).
+//
+// Bias mode 3 (T5 relative-position bias computed in the kernel, see attn_fwd.cu): the per-head band of bias values
+// lives in the shared memory of the dense bias halves; dS takes the same route as for a dense (1, H, M, N) bias.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -359,6 +362,14 @@ attn_bwd_kernel_v2(const __grid_constant__ AttnBwdKernelParams p) {
             bulk_commit_group();
         };
 
+        const float* band = reinterpret_cast<const float*>(smem + C::kBias);   // [bias mode 3]
+        if (kBiasMode == 3) {
+            float* dst = reinterpret_cast<float*>(smem + C::kBias);
+            const float* src = p.rpe.band + (int64_t)h * p.rpe.band_len;
+            for (int i = ctid; i < p.rpe.band_len; i += 256) dst[i] = __ldg(src + i);
+            named_bar_sync(3, 256);
+        }
+
         // row statistics are prefetched one block ahead (global latency off the critical path)
         float L_next = 0.f, dlt_next = 0.f;
         if (n_iter > 0 && i_start * kBM + r < p.M) {
@@ -383,6 +394,16 @@ attn_bwd_kernel_v2(const __grid_constant__ AttnBwdKernelParams p) {
                 lim = cl < lim ? cl : lim;
             }
             const bool need_mask = (col0 + kBN > p.N) || (kCausal && (col0 + kBN - 1 > mrow0 + pseq));
+            // bias mode 3: relative positions n - m of this tile are [col0 - mrow0 - 127, col0 - mrow0 + 127]
+            bool rpe_const = false;
+            float rpe_cval = 0.f;
+            if (kBiasMode == 3) {
+                const int rel_min = col0 - mrow0 - (kBM - 1);
+                const int rel_max = col0 - mrow0 + (kBN - 1);
+                rpe_const = rel_max <= p.rpe.const_lo || rel_min >= p.rpe.const_hi;
+                if (rpe_const)
+                    rpe_cval = band[(rel_max <= p.rpe.const_lo ? p.rpe.const_lo : p.rpe.const_hi) - p.rpe.band_lo];
+            }
 
             // ---------------- [B] P and dS of this block, in registers ----------------
             if (ctid == 0) BWD_TS(0, k, 0);
@@ -422,6 +443,15 @@ attn_bwd_kernel_v2(const __grid_constant__ AttnBwdKernelParams p) {
                     for (int e = 0; e < 32; ++e) {
                         const int c = col0 + wg * 64 + ch * 32 + e;
                         bv[e] = (row_ok && c < p.N) ? to_float16bit<kBf16>(__ldg(bp + (int64_t)c * p.bias_sn)) : 0.f;
+                    }
+                } else if (kBiasMode == 3) {
+                    if (rpe_const) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) bv[e] = rpe_cval;
+                    } else {
+                        const float* bp = band + (col0 + wg * 64 + ch * 32 - grow - p.rpe.band_lo);
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) bv[e] = bp[e];
                     }
                 } else {
 #pragma unroll
@@ -589,7 +619,10 @@ static cudaError_t launch_bwd2_d(const AttnBwdKernelParams& kp, int bias_mode, b
         case 2: return launch_bwd2_inst<kD, kBf16, 1, false>(kp, stream);
         case 3: return launch_bwd2_inst<kD, kBf16, 1, true>(kp, stream);
         case 4: return launch_bwd2_inst<kD, kBf16, 2, false>(kp, stream);
-        default: return launch_bwd2_inst<kD, kBf16, 2, true>(kp, stream);
+        case 5: return launch_bwd2_inst<kD, kBf16, 2, true>(kp, stream);
+        case 6: return launch_bwd2_inst<kD, kBf16, 3, false>(kp, stream);
+        case 7: return launch_bwd2_inst<kD, kBf16, 3, true>(kp, stream);
+        default: return cudaErrorInvalidValue;
     }
 }
 

@@ -12,6 +12,12 @@
 //                      rescale of O in TMEM), P -> TMEM as packed 16-bit, epilogue O / l and LSE
 //
 // TMEM columns: S [0,128) fp32 | O [128,128+D) fp32 | P [128+D, 128+D+64) packed 16-bit pairs.
+//
+// Bias modes: 0 none | 1 dense bias through TMA | 2 dense bias through pointers (rows not 16-byte aligned) |
+// 3 T5 relative-position bias computed in the kernel (the reference's `fa2_rpe` surface,
+//   /root/reference/src/model/modeling_flash_t5.py:275-279): the per-head band of bias values over relative
+//   positions sits in shared memory (where modes 1/2 keep the bias ring); tiles whose relative positions are all
+//   beyond the last distinct bucket add one scalar, the others read band[n - m] -- no (H, M, N) tensor exists.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -254,6 +260,14 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdKernelParams p) {
         float m_ref = -INFINITY;   // running reference max (natural units, scaled + biased scores)
         float l_sum = 0.f;
 
+        const float* band = reinterpret_cast<const float*>(smem + L::kBias);   // [bias mode 3]
+        if (kBiasMode == 3) {
+            float* dst = reinterpret_cast<float*>(smem + L::kBias);
+            const float* src = p.rpe.band + (int64_t)h * p.rpe.band_len;
+            for (int i = threadIdx.x; i < p.rpe.band_len; i += 128) dst[i] = __ldg(src + i);
+            named_bar_sync(1, 128);
+        }
+
         const uint16_t* bias_row = nullptr;
         if (kBiasMode == 2) {
             bias_row = reinterpret_cast<const uint16_t*>(p.bias) + (p.bias_b_bcast ? 0 : (int64_t)b * p.bias_sb) +
@@ -312,6 +326,19 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdKernelParams p) {
                     if (grow < p.M && col0 + c < p.N)
                         bv = to_float16bit<kBf16>(__ldg(bias_row + (int64_t)(col0 + c) * p.bias_sn));
                     x[c] = fmaf(x[c], p.sm_scale, bv);
+                }
+            } else if (kBiasMode == 3) {
+                // relative positions n - m of this tile: [col0 - row0 - 127, col0 - row0 + 127]
+                const int rel_min = col0 - row0 - (kBM - 1);
+                const int rel_max = col0 - row0 + (kBN - 1);
+                if (rel_max <= p.rpe.const_lo || rel_min >= p.rpe.const_hi) {
+                    const float bv = band[(rel_max <= p.rpe.const_lo ? p.rpe.const_lo : p.rpe.const_hi) - p.rpe.band_lo];
+#pragma unroll
+                    for (int c = 0; c < kBN; ++c) x[c] = fmaf(x[c], p.sm_scale, bv);
+                } else {
+                    const float* bp = band + (col0 - grow - p.rpe.band_lo);
+#pragma unroll
+                    for (int c = 0; c < kBN; ++c) x[c] = fmaf(x[c], p.sm_scale, bp[c]);
                 }
             } else {
 #pragma unroll
@@ -472,7 +499,10 @@ static cudaError_t launch_fwd_d(const AttnFwdKernelParams& kp, int bias_mode, bo
         case 2: return launch_fwd_inst<kD, kBf16, 1, false>(kp, stream);
         case 3: return launch_fwd_inst<kD, kBf16, 1, true>(kp, stream);
         case 4: return launch_fwd_inst<kD, kBf16, 2, false>(kp, stream);
-        default: return launch_fwd_inst<kD, kBf16, 2, true>(kp, stream);
+        case 5: return launch_fwd_inst<kD, kBf16, 2, true>(kp, stream);
+        case 6: return launch_fwd_inst<kD, kBf16, 3, false>(kp, stream);
+        case 7: return launch_fwd_inst<kD, kBf16, 3, true>(kp, stream);
+        default: return cudaErrorInvalidValue;
     }
 }
 

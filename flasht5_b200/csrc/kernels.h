@@ -8,6 +8,19 @@
 
 namespace b200t5 {
 
+// Bias mode 3: bias[h, m, n] = band[h][(n - m) - band_lo], a Toeplitz bias given as one fp32 row per head over
+// the relative positions band_lo .. band_lo + band_len - 1 (values already rounded to the io dtype).  Every
+// rel <= const_lo shares the value at const_lo and every rel >= const_hi the value at const_hi, so a 128x128 tile
+// whose relative positions all lie on one side needs no per-element lookup.  band_lo = const_lo - 255 and
+// band_len = const_hi - const_lo + 511: any tile that is not constant stays inside the band.
+struct RpeBand {
+    const float* band;      // (H, band_len) fp32
+    int band_lo, band_len;
+    int const_lo, const_hi;
+};
+constexpr int kRpeBandPad = 255;        // 2 * 128 - 1 relative positions per tile
+constexpr int kRpeMaxBandLen = 8192;    // 32 KB of shared memory (the dense bias ring's space)
+
 struct AttnFwdKernelParams {
     CUtensorMap map_q;      // (D, M, H, B)   box (min(D,64), 128, 1, 1)
     CUtensorMap map_k;      // (D, N, H, B)
@@ -22,6 +35,8 @@ struct AttnFwdKernelParams {
     int num_m_blocks;
     int bias_b_bcast, bias_h_bcast;
     float sm_scale;
+    // in-kernel T5 relative-position bias                                     [bias mode 3]
+    RpeBand rpe;
 };
 
 struct AttnBwdKernelParams {
@@ -50,6 +65,8 @@ struct AttnBwdKernelParams {
     // dQ surface: key block nb adds its partial dQ tile (rounded to the io dtype) into group nb % dq_groups;
     // groups hold <= 4 key blocks each and are summed in fp32 by the convert kernel.
     int dq_groups;
+    // in-kernel T5 relative-position bias                                     [bias mode 3]
+    RpeBand rpe;
 };
 
 cudaError_t launch_attn_fwd(const AttnFwdKernelParams& kp, int D, bool bf16, int bias_mode, bool causal,
@@ -101,6 +118,11 @@ cudaError_t launch_t5_bias_fwd(const void* table, const int32_t* lut, int lut_ze
 cudaError_t launch_t5_bias_bwd(const void* dbias, const int32_t* lut, int lut_zero, int lut_len, const int32_t* ctx_pos,
                                const int32_t* mem_pos, float* dtable, int H, int M, int N, int num_buckets, int dbias_dtype,
                                cudaStream_t stream);
+
+// Band of bias values for bias mode 3 (RpeBand): band[h][j] = io_round(table[lut[clamp(band_lo + j + lut_zero)], h]).
+cudaError_t launch_rpe_band(const void* table, int64_t stride_b, int64_t stride_h, int table_dtype, const int32_t* lut,
+                            int lut_zero, int lut_len, float* band, int H, int band_lo, int band_len, int io_dtype,
+                            cudaStream_t stream);
 
 // Launch counter (every kernel launched by this library bumps it; read through the C ABI).
 void count_launch(int n = 1);

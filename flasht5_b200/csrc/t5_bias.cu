@@ -311,6 +311,40 @@ cudaError_t launch_t5_bias_fwd(const void* table, const int32_t* lut, int lut_ze
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------
+// band of bias values over relative positions for the in-kernel bias mode of the attention kernels
+// (kernels.h: RpeBand):  band[h][j] = io_round(table[lut[clamp(band_lo + j + lut_zero)], h])  as fp32
+// ------------------------------------------------------------------------------------------
+template <int kTabDt>
+__global__ void __launch_bounds__(256) rpe_band_kernel(const void* __restrict__ table, int64_t stride_b, int64_t stride_h,
+                                                       const int32_t* __restrict__ lut, int lut_zero, int lut_len,
+                                                       float* __restrict__ band, int band_lo, int band_len, int io_dtype) {
+    const int h = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= band_len) return;
+    int idx = band_lo + j + lut_zero;
+    idx = idx < 0 ? 0 : (idx >= lut_len ? lut_len - 1 : idx);
+    const int bucket = __ldg(lut + idx);
+    float v = ld_elem<kTabDt>(table, (int64_t)bucket * stride_b + (int64_t)h * stride_h);
+    // the dense path hands the kernels a bias already cast to the attention dtype: round the same way
+    if (io_dtype == 1) v = to_float16bit<true>(static_cast<uint16_t>(pack2<true>(v, 0.f) & 0xFFFFu));
+    else if (io_dtype == 0) v = to_float16bit<false>(static_cast<uint16_t>(pack2<false>(v, 0.f) & 0xFFFFu));
+    band[(int64_t)h * band_len + j] = v;
+}
+
+cudaError_t launch_rpe_band(const void* table, int64_t stride_b, int64_t stride_h, int table_dtype, const int32_t* lut,
+                            int lut_zero, int lut_len, float* band, int H, int band_lo, int band_len, int io_dtype,
+                            cudaStream_t stream) {
+    const dim3 grid((band_len + 255) / 256, H);
+    switch (table_dtype) {
+        case 0: rpe_band_kernel<0><<<grid, 256, 0, stream>>>(table, stride_b, stride_h, lut, lut_zero, lut_len, band, band_lo, band_len, io_dtype); break;
+        case 1: rpe_band_kernel<1><<<grid, 256, 0, stream>>>(table, stride_b, stride_h, lut, lut_zero, lut_len, band, band_lo, band_len, io_dtype); break;
+        default: rpe_band_kernel<2><<<grid, 256, 0, stream>>>(table, stride_b, stride_h, lut, lut_zero, lut_len, band, band_lo, band_len, io_dtype); break;
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
 cudaError_t launch_t5_bias_bwd(const void* dbias, const int32_t* lut, int lut_zero, int lut_len, const int32_t* ctx_pos,
                                const int32_t* mem_pos, float* dtable, int H, int M, int N, int num_buckets, int dbias_dtype,
                                cudaStream_t stream) {

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B200T5_ABI_VERSION 1
+#define B200T5_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define B200T5_API __attribute__((visibility("default")))
@@ -141,6 +141,45 @@ B200T5_API int b200t5_t5_bias_fwd(const void* table, const int32_t* lut, int32_t
 B200T5_API int b200t5_t5_bias_bwd(const void* dbias, const int32_t* lut, int32_t lut_zero, int32_t lut_len,
                                   const int32_t* ctx_pos, const int32_t* mem_pos, float* dtable, int32_t H, int32_t M,
                                   int32_t N, int32_t num_buckets, int dbias_dtype, int device, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Attention with the T5 relative-position bias computed inside the kernels (no (1,H,M,N) bias tensor, no
+ * (1,H,M,N) gradient handed back): the operator behind the reference's `attention_type == "fa2_rpe"` call
+ *   src/model/modeling_flash_t5.py:275-279  flash_attn_func(q, k, v, softmax_scale=..., causal=...,
+ *       rpe_weights=relative_attention_bias.weight.t(), rpe_max_distance=...)
+ * (the flash-attention fork that implements it is not part of the reference checkout; the semantics are those of
+ * the dense path with bias = RelativePositionalEncoding.compute_bias(M, N), src/utils/positional_encoding.py:73-102,
+ * cast to the q dtype, and dtable = the gradient that autograd would scatter back into the embedding table).
+ *
+ * bias[h, m, n] = table[lut[(n - m) + lut_zero], h].  The caller passes the bucket lookup table (built with the
+ * reference formula :25-71) and the two relative positions beyond which it is constant:
+ *   every rel <= const_lo has lut == lut[const_lo + lut_zero]; every rel >= const_hi has lut == lut[const_hi + lut_zero]
+ *   (const_lo < const_hi; -(M-1) <= const_lo and const_hi <= N-1 always qualify).
+ * `band` is a caller-allocated fp32 buffer of H * b200t5_rpe_band_len(const_lo, const_hi) elements:
+ * b200t5_rpe_band() fills it (bias per head over the relative positions const_lo-255 .. const_hi+255, rounded to
+ * the attention dtype), b200t5_attn_rpe_fwd / _bwd read it.  One band serves every layer that shares the table.
+ * Limits: band_len <= 8192 (B200T5_ERR_UNSUPPORTED otherwise: use the dense path), num_buckets <= 256.
+ * b200t5_attn_rpe_fwd / _bwd take the same b200t5_attn_params as the dense entry points with bias == NULL and
+ * dbias == NULL; _bwd additionally writes dtable (num_buckets, H) fp32 row-major (overwritten) and needs a
+ * workspace of b200t5_attn_rpe_bwd_workspace_bytes() bytes.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct b200t5_rpe_params {
+    const void* table;             /* element (bucket, head) at table[bucket * table_stride_b + head * table_stride_h] */
+    int64_t table_stride_b, table_stride_h;
+    int32_t table_dtype;           /* B200T5_F16 | B200T5_BF16 | B200T5_F32 */
+    int32_t num_buckets;
+    const int32_t* lut;            /* int32[lut_len]; must cover rel in [-(M-1), N-1] */
+    int32_t lut_zero, lut_len;
+    int32_t const_lo, const_hi;
+    float* band;                   /* (H, band_len) fp32 */
+    float* dtable;                 /* backward only */
+} b200t5_rpe_params;
+
+B200T5_API int b200t5_rpe_band_len(int32_t const_lo, int32_t const_hi);
+B200T5_API int b200t5_rpe_band(const b200t5_rpe_params* r, int32_t H, int io_dtype, int device, void* stream);
+B200T5_API int b200t5_attn_rpe_fwd(const b200t5_attn_params* p, const b200t5_rpe_params* r);
+B200T5_API size_t b200t5_attn_rpe_bwd_workspace_bytes(const b200t5_attn_params* p, const b200t5_rpe_params* r);
+B200T5_API int b200t5_attn_rpe_bwd(const b200t5_attn_params* p, const b200t5_rpe_params* r);
 
 /* ------------------------------------------------------------------------------------------------
  * Library state

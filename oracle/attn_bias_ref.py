@@ -179,3 +179,37 @@ def t5_bias(table: torch.Tensor, M: int, N: int, bidirectional=True, num_buckets
     buckets = t5_relative_position_bucket(mem - ctx, bidirectional, num_buckets, max_distance)
     vals = table[buckets]                    # (M, N, H)
     return vals.permute(2, 0, 1).unsqueeze(0).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------
+# Attention with the T5 bias taken straight from the embedding table (the reference's "fa2_rpe" surface,
+# src/model/modeling_flash_t5.py:275-279).  The flash-attention fork behind that call is not in the reference
+# checkout, so the oracle restates the reference's own dense composition: compute_bias (:73-102 of
+# src/utils/positional_encoding.py) -> cast to the attention dtype -> attention -> and, backwards, the
+# embedding's scatter-add of dBias into the (num_buckets, H) table.
+# ---------------------------------------------------------------------------------------------
+def t5_dtable(dbias: torch.Tensor, M: int, N: int, bidirectional=True, num_buckets=32, max_distance=128) -> torch.Tensor:
+    """dbias (1, H, M, N) -> dtable (num_buckets, H): sum of dbias over the positions of each bucket."""
+    ctx = torch.arange(M).unsqueeze(-1)
+    mem = torch.arange(N).unsqueeze(0)
+    buckets = t5_relative_position_bucket(mem - ctx, bidirectional, num_buckets, max_distance)   # (M, N)
+    H = dbias.shape[1]
+    dtable = torch.zeros(num_buckets, H, dtype=dbias.dtype)
+    dtable.index_add_(0, buckets.reshape(-1), dbias[0].permute(1, 2, 0).reshape(M * N, H))
+    return dtable
+
+
+def attn_rpe_fwd_bwd(q, k, v, table, do, causal=False, sm_scale=None, bidirectional=None, num_buckets=None,
+                     max_distance=128, bias_dtype=None, dtype=torch.float64):
+    """-> (o, L, dq, dk, dv, dtable).  table: (num_buckets, H).  bias_dtype: round the gathered bias to this dtype
+    first (what the dense path does when it casts the bias to the q dtype); None keeps it exact."""
+    M, N = q.shape[2], k.shape[2]
+    if bidirectional is None:
+        bidirectional = not causal
+    if num_buckets is None:
+        num_buckets = table.shape[0]
+    bias = t5_bias(table, M, N, bidirectional, num_buckets, max_distance)
+    if bias_dtype is not None:
+        bias = bias.to(bias_dtype)
+    o, L, dq, dk, dv, dbias = attn_fwd_bwd(q, k, v, bias.to(dtype), do, causal, sm_scale, dtype=dtype)
+    return o, L, dq, dk, dv, t5_dtable(dbias, M, N, bidirectional, num_buckets, max_distance)

@@ -205,8 +205,49 @@ def gen_t5_bias():
         print(f"t5bias_{name}: ok")
 
 
+# name: (B,H,M,N,D, causal, sm_scale, num_buckets, max_distance)
+RPE_CASES = {
+    "enc_300x300": (2, 3, 300, 300, 32, False, 1.0, 32, 128),        # constant tiles on both sides + the band
+    "dec_causal_200x200": (1, 2, 200, 200, 64, True, 1.0, 32, 128),  # unidirectional buckets, causal mask
+    "cross_shape_70x330_nb16": (2, 2, 70, 330, 16, False, 0.25, 16, 64),   # M != N, other bucket geometry
+}
+
+
+def gen_attn_rpe():
+    """The reference's dense composition of the fa2_rpe semantics: RelativePositionalEncoding.compute_bias ->
+    attn_ref(upcast=True) -> autograd down to the embedding weight (the (num_buckets, H) table)."""
+    for i, (name, (B, H, M, N, D, causal, scale, nb, maxd)) in enumerate(RPE_CASES.items()):
+        rng = np.random.default_rng(300 + i)
+        q = bf16_exact(rng.standard_normal((B, H, M, D)))
+        k = bf16_exact(rng.standard_normal((B, H, N, D)))
+        v = bf16_exact(rng.standard_normal((B, H, N, D)))
+        do = bf16_exact(rng.standard_normal((B, H, M, D)))
+        table = bf16_exact(0.5 * rng.standard_normal((nb, H)))
+        pe = RelativePositionalEncoding(nb, maxd, H, max(M, N), bidirectional=not causal)
+        with torch.no_grad():
+            pe.relative_attention_bias.weight.copy_(table)
+        qs, ks, vs = (t.clone().requires_grad_(True) for t in (q, k, v))
+        bias = pe.compute_bias(M, N)
+        o = attn_ref(qs, ks, vs, bias, scale, causal=causal, upcast=True)
+        dq, dk, dv, dtable = torch.autograd.grad(o, [qs, ks, vs, pe.relative_attention_bias.weight], do)
+        oo, LL, odq, odk, odv, odt = attn_bias_ref.attn_rpe_fwd_bwd(q, k, v, table, do, causal, scale, num_buckets=nb,
+                                                                    max_distance=maxd)
+        for nm, a, b_ in (("o", oo, o.detach()), ("dq", odq, dq), ("dk", odk, dk), ("dv", odv, dv), ("dtable", odt, dtable)):
+            mx, rf = attn_bias_ref.error_metrics(a, b_)
+            assert rf < 2e-6 and mx < 1e-5 * (1 + b_.abs().max().item()), (name, nm, mx, rf)
+        np.savez_compressed(os.path.join(GOLD, f"rpe_{name}.npz"), q=q.numpy(), k=k.numpy(), v=v.numpy(), do=do.numpy(),
+                            table=table.numpy(), o=o.detach().numpy(), dq=dq.numpy(), dk=dk.numpy(), dv=dv.numpy(),
+                            dtable=dtable.numpy(), causal=np.array(causal), sm_scale=np.array(scale, dtype=np.float64),
+                            num_buckets=np.array(nb), max_distance=np.array(maxd))
+        print(f"rpe_{name}: ok  (oracle==reference)")
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
+    if "--only-rpe" in sys.argv:
+        gen_attn_rpe()
+        sys.exit(0)
+    gen_attn_rpe()
     gen_t5_bias()
     gen_buckets()
     gen_attn()
