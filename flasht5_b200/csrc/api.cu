@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -204,9 +205,17 @@ static int bias_mode_of(const b200t5_attn_params* p) {
 }
 
 static int round_up8(int x) { return (x + 7) / 8 * 8; }
+constexpr bool kFwdPersistentDefault = false;
 static int check_dtype3(int dt, const char* what) {
     if (dt == B200T5_F16 || dt == B200T5_BF16 || dt == B200T5_F32) return 0;
     return fail(B200T5_ERR_UNSUPPORTED, "%s dtype %d not in {fp16, bf16, fp32}", what, dt);
+}
+
+// Forward schedule: B200T5_FWD_PERSIST=0/1 selects one-CTA-per-block (attn_fwd.cu) or persistent (attn_fwd_persist.cu);
+// read on every call so that a developer A/B script can flip it inside one process.
+static bool fwd_persistent_enabled() {
+    const char* v = getenv("B200T5_FWD_PERSIST");
+    return v ? atoi(v) != 0 : kFwdPersistentDefault;
 }
 
 // ---- in-kernel relative-position bias (bias mode 3) ----
@@ -283,7 +292,10 @@ static int attn_fwd_impl(const b200t5_attn_params* p, const b200t5_rpe_params* r
     cudaError_t e;
     {
         ProfScope prof(B200T5_KERNEL_ATTN_FWD, static_cast<cudaStream_t>(p->stream));
-        e = launch_attn_fwd(kp, p->D, p->dtype == B200T5_BF16, mode, p->causal != 0, static_cast<cudaStream_t>(p->stream));
+        // the persistent schedule covers the TMA / in-kernel bias modes; the pointer path (mode 2) keeps one CTA per block
+        const bool persist = fwd_persistent_enabled() && mode != 2;
+        e = persist ? launch_attn_fwd_persist(kp, p->D, p->dtype == B200T5_BF16, mode, p->causal != 0, static_cast<cudaStream_t>(p->stream))
+                    : launch_attn_fwd(kp, p->D, p->dtype == B200T5_BF16, mode, p->causal != 0, static_cast<cudaStream_t>(p->stream));
     }
     if (e != cudaSuccess) return fail_cuda(e, "attn_fwd launch");
     return 0;

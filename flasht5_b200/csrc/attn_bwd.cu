@@ -170,7 +170,7 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdKernelParams p) {
             for (int k = 0; k < n_iter; ++k) {
                 const int s = k % C::kQStages;
                 const int mrow0 = (i_start + k) * kBM;
-                mbar_wait(qdo_empty + s, ((k / C::kQStages) & 1) ^ 1);
+                mbar_wait_producer(qdo_empty + s, ((k / C::kQStages) & 1) ^ 1);
                 mbar_arrive_expect_tx(qdo_full + s, 2 * C::kTileBytes);
 #pragma unroll
                 for (int bx = 0; bx < C::kBoxes; ++bx) {
@@ -187,7 +187,7 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdKernelParams p) {
                 const int mrow0 = (i_start + k) * kBM;
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
-                    mbar_wait(b_empty + hh, (k & 1) ^ 1);
+                    mbar_wait_producer(b_empty + hh, (k & 1) ^ 1);
                     mbar_arrive_expect_tx(b_full + hh, kHalfBytes);
                     tma_load_4d(smem + C::kBias + hh * kHalfBytes, &p.map_bias, b_full + hh, col0 + hh * 64, mrow0, hb,
                                 bb);

@@ -196,7 +196,7 @@ attn_bwd_kernel_v2(const __grid_constant__ AttnBwdKernelParams p) {
             for (int k = 0; k < n_iter; ++k) {
                 const int s = k % C::kQStages;
                 const int mrow0 = (i_start + k) * kBM;
-                mbar_wait(qdo_empty + s, ((k / C::kQStages) & 1) ^ 1);
+                mbar_wait_producer(qdo_empty + s, ((k / C::kQStages) & 1) ^ 1);
                 mbar_arrive_expect_tx(qdo_full + s, 2 * C::kTileBytes);
                 tma_load_4d(smem + C::kQ + s * C::kTileBytes, &p.map_q, qdo_full + s, 0, mrow0, h, b);
                 tma_load_4d(smem + C::kDO + s * C::kTileBytes, &p.map_do, qdo_full + s, 0, mrow0, h, b);
@@ -208,7 +208,7 @@ attn_bwd_kernel_v2(const __grid_constant__ AttnBwdKernelParams p) {
                 const int mrow0 = (i_start + k) * kBM;
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
-                    mbar_wait(b_empty + hh, (k & 1) ^ 1);
+                    mbar_wait_producer(b_empty + hh, (k & 1) ^ 1);
                     mbar_arrive_expect_tx(b_full + hh, kHalfBytes);
                     tma_load_4d(smem + C::kBias + hh * kHalfBytes, &p.map_bias, b_full + hh, col0 + hh * 64, mrow0, hb,
                                 bb);

@@ -72,6 +72,26 @@ struct FwdBars {
 
 }  // namespace
 
+// Developer build (-DB200T5_FWD_TIMING): every CTA that lands on SM `kTimedSm` stamps clock64 at the phase
+// boundaries of softmax thread 0 and of the MMA warp; the launcher prints the timeline.  Off in the product build.
+#ifdef B200T5_FWD_TIMING
+constexpr int kTimedSm = 17;
+__device__ int g_fwd_ts_slots;
+__device__ long long g_fwd_ts[32][2][12][8];   // [slot][role][tile][stamp]
+__device__ int g_fwd_ts_bid[32];
+__device__ __forceinline__ long long clk64() {
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+    return t;
+}
+#define FWD_TS(role, j, slot_)                                                              \
+    do {                                                                                    \
+        if (ts_slot >= 0 && (j) < 12) g_fwd_ts[ts_slot][role][j][slot_] = clk64();          \
+    } while (0)
+#else
+#define FWD_TS(role, j, slot_) do { } while (0)
+#endif
+
 template <int kD, bool kBf16, int kBiasMode, bool kCausal>
 __global__ void __launch_bounds__(256, 2)   // 128 regs at launch; setmaxnreg re-splits them per role
 attn_fwd_kernel(const __grid_constant__ AttnFwdKernelParams p) {
@@ -148,6 +168,28 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdKernelParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+#ifdef B200T5_FWD_TIMING
+    int ts_slot = -1;
+    {
+        // (no static shared memory: 4 static bytes pad to 1 KB in front of the 1024-aligned dynamic block and cost
+        //  the second resident CTA; the TMEM slot has spare words)
+        volatile int& s_ts_slot = *reinterpret_cast<volatile int*>(smem + L::kTmemSlot + 8);
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        if (threadIdx.x == 0) {
+            s_ts_slot = -1;
+            if (smid == kTimedSm) {
+                const int sl = atomicAdd(&g_fwd_ts_slots, 1);
+                if (sl < 32) {
+                    s_ts_slot = sl;
+                    g_fwd_ts_bid[sl] = blockIdx.x;
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 || (warp == 5 && lane == 0)) ts_slot = s_ts_slot;
+    }
+#endif
 
     if (warp >= 4) {
         // =============================== control warps ===============================
@@ -161,13 +203,13 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdKernelParams p) {
             for (int j = 0; j < num_tiles; ++j) {
                 const int s = j % kKVStages;
                 const uint32_t par = ((j / kKVStages) & 1) ^ 1;
-                mbar_wait(bars.k_empty + s, par);
+                mbar_wait_producer(bars.k_empty + s, par);
                 mbar_arrive_expect_tx(bars.k_full + s, L::kTileBytes);
 #pragma unroll
                 for (int bx = 0; bx < L::kBoxes; ++bx)
                     tma_load_4d(smem + L::kK + s * L::kTileBytes + bx * L::kBoxBytes, &p.map_k, bars.k_full + s,
                                 bx * 64, j * kBN, h, b);
-                mbar_wait(bars.v_empty + s, par);
+                mbar_wait_producer(bars.v_empty + s, par);
                 mbar_arrive_expect_tx(bars.v_full + s, L::kTileBytes);
 #pragma unroll
                 for (int bx = 0; bx < L::kBoxes; ++bx)
@@ -181,7 +223,7 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdKernelParams p) {
             for (int it = 0; it < 2 * num_tiles; ++it) {
                 const int s = it % kBiasStages;
                 const uint32_t par = ((it / kBiasStages) & 1) ^ 1;
-                mbar_wait(bars.b_empty + s, par);
+                mbar_wait_producer(bars.b_empty + s, par);
                 mbar_arrive_expect_tx(bars.b_full + s, kBiasHalfBytes);
                 tma_load_4d(smem + L::kBias + s * kBiasHalfBytes, &p.map_bias, bars.b_full + s,
                             (it >> 1) * kBN + (it & 1) * 64, row0, hb, bb);
@@ -227,12 +269,15 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdKernelParams p) {
                     mbar_wait(bars.k_full + (jn % kKVStages), (jn / kKVStages) & 1);
                     mbar_wait(bars.s_empty, j & 1);
                     tc_fence_after();
+                    FWD_TS(1, jn, 0);
                     issue_s(jn);
+                    FWD_TS(1, jn, 1);
                 }
                 const int s = j % kKVStages;
                 mbar_wait(bars.v_full + s, (j / kKVStages) & 1);
                 mbar_wait(bars.p_full, j & 1);
                 tc_fence_after();
+                FWD_TS(1, j, 2);
                 const uint32_t v_lo = v_lo0 + s * (L::kTileBytes >> 4);
                 if (leader) {
 #pragma unroll
@@ -245,6 +290,7 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdKernelParams p) {
                     umma_commit(bars.v_empty + s);
                 }
                 __syncwarp();
+                FWD_TS(1, j, 3);
             }
         }
     } else {
@@ -278,8 +324,10 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdKernelParams p) {
             const int col0 = j * kBN;
             float x[kBN];
 
+            FWD_TS(0, j, 0);
             mbar_wait(bars.s_full, j & 1);
             tc_fence_after();
+            FWD_TS(0, j, 1);
             {
                 uint32_t(&xr)[kBN] = reinterpret_cast<uint32_t(&)[kBN]>(x);
                 tmem_ld32(tm_s + 0, reinterpret_cast<uint32_t(&)[32]>(xr[0]));
@@ -291,6 +339,7 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdKernelParams p) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bars.s_empty);
+            FWD_TS(0, j, 2);
 
             // ---- scores = S * sm_scale + bias ----
             if (kBiasMode == 1) {
@@ -345,6 +394,7 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdKernelParams p) {
                 for (int c = 0; c < kBN; ++c) x[c] *= p.sm_scale;
             }
 
+            FWD_TS(0, j, 3);
             // ---- masks: key tail and (bottom-right aligned) causal ----
             {
                 int lim = p.N - col0;
@@ -377,6 +427,7 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdKernelParams p) {
             }
             const float m_safe = (m_ref == -INFINITY) ? 0.f : m_ref;
             const float neg_m_log2 = -m_safe * kLog2e;
+            FWD_TS(0, j, 4);
 
             uint32_t pk[kBN / 2];
             float s0 = 0.f, s1 = 0.f;
@@ -389,6 +440,7 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdKernelParams p) {
                 pk[c / 2] = pack2<kBf16>(e0, e1);
             }
             l_sum = l_sum * alpha + (s0 + s1);
+            FWD_TS(0, j, 5);
 
             if (j > 0) {
                 mbar_wait(bars.pv_done, (j - 1) & 1);     // O and the P buffer are free again
@@ -414,12 +466,14 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdKernelParams p) {
                     }
                 }
             }
+            FWD_TS(0, j, 6);
             tmem_st32(tm_p + 0, reinterpret_cast<const uint32_t(&)[32]>(pk[0]));
             tmem_st32(tm_p + 32, reinterpret_cast<const uint32_t(&)[32]>(pk[32]));
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bars.p_full);
+            FWD_TS(0, j, 7);
         }
 
         // ---- epilogue: O / l -> global (row-contiguous 16-byte stores), LSE ----
@@ -478,6 +532,22 @@ static cudaError_t launch_fwd_inst(const AttnFwdKernelParams& kp, cudaStream_t s
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     if (e != cudaSuccess) return e;
     const int grid = kp.B * kp.H * kp.num_m_blocks;
+    // two CTAs per SM need the full shared-memory carveout; ask for it instead of leaving it to the driver's heuristic
+    static const int carveout = getenv("B200T5_DEBUG_FWD_CARVEOUT") ? atoi(getenv("B200T5_DEBUG_FWD_CARVEOUT")) : -2;
+    if (carveout >= -1) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
+        if (e != cudaSuccess) return e;
+    }
+#ifdef B200T5_FWD_TIMING
+    {
+        int nb = -1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 256, L::kTotal);
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, kern);
+        printf("FWD_TIMING occupancy API: %d CTAs/SM; regs %d, static smem %zu, dynamic %d, carveout pref %d (env %d)\n", nb,
+               fa.numRegs, fa.sharedSizeBytes, (int)L::kTotal, fa.preferredShmemCarveout, carveout);
+    }
+#endif
     static const int extra_smem = getenv("B200T5_DEBUG_EXTRA_SMEM") ? atoi(getenv("B200T5_DEBUG_EXTRA_SMEM")) : 0;
     if (extra_smem > 0) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal + extra_smem);
@@ -486,8 +556,42 @@ static cudaError_t launch_fwd_inst(const AttnFwdKernelParams& kp, cudaStream_t s
         count_launch();
         return cudaGetLastError();
     }
+#ifdef B200T5_FWD_TIMING
+    {
+        int zero = 0;
+        cudaMemcpyToSymbol(g_fwd_ts_slots, &zero, sizeof(int));
+    }
+#endif
     kern<<<grid, 256, L::kTotal, stream>>>(kp);
     count_launch();
+#ifdef B200T5_FWD_TIMING
+    {
+        cudaDeviceSynchronize();
+        static long long ts[32][2][12][8];
+        int bids[32], n = 0;
+        cudaMemcpyFromSymbol(ts, g_fwd_ts, sizeof(ts));
+        cudaMemcpyFromSymbol(bids, g_fwd_ts_bid, sizeof(bids));
+        cudaMemcpyFromSymbol(&n, g_fwd_ts_slots, sizeof(int));
+        if (n > 32) n = 32;
+        const int tiles = (kp.N + kBN - 1) / kBN < 12 ? (kp.N + kBN - 1) / kBN : 12;
+        long long t0 = n > 0 ? ts[0][0][0][0] : 0;
+        for (int s = 0; s < n; ++s)
+            if (ts[s][0][0][0] < t0) t0 = ts[s][0][0][0];
+        printf("FWD_TIMING sm %d: %d CTAs; softmax thread 0: [wait S, S ready, S in regs, bias added, max done, exp done, PV(j-1) done, P stored]; "
+               "mma: [S(j) issue start, S(j) issued, P(j) ready, PV(j) issued]\n", kTimedSm, n);
+        for (int s = 0; s < n; ++s) {
+            printf(" CTA slot %d (block %d)\n", s, bids[s]);
+            for (int j = 0; j < tiles; ++j) {
+                printf("  j=%d sm:", j);
+                for (int q = 0; q < 8; ++q) printf(" %7lld", ts[s][0][j][q] - t0);
+                printf("   mma:");
+                for (int q = 0; q < 4; ++q) printf(" %7lld", ts[s][1][j][q] - t0);
+                printf("\n");
+            }
+        }
+        fflush(stdout);
+    }
+#endif
     return cudaGetLastError();
 }
 
@@ -508,6 +612,15 @@ static cudaError_t launch_fwd_d(const AttnFwdKernelParams& kp, int bias_mode, bo
 
 cudaError_t launch_attn_fwd(const AttnFwdKernelParams& kp, int D, bool bf16, int bias_mode, bool causal,
                             cudaStream_t stream) {
+#ifdef B200T5_FWD_TIMING
+    // the timing build only carries the headline instantiations (D = 64, bf16, non-causal)
+    if (D == 64 && bf16 && !causal) {
+        if (bias_mode == 0) return launch_fwd_inst<64, true, 0, false>(kp, stream);
+        if (bias_mode == 1) return launch_fwd_inst<64, true, 1, false>(kp, stream);
+        if (bias_mode == 3) return launch_fwd_inst<64, true, 3, false>(kp, stream);
+    }
+    return cudaErrorInvalidValue;
+#else
 #define B200T5_FWD_CASE(DD)                                                              \
     case DD:                                                                             \
         return bf16 ? launch_fwd_d<DD, true>(kp, bias_mode, causal, stream)              \
@@ -520,6 +633,7 @@ cudaError_t launch_attn_fwd(const AttnFwdKernelParams& kp, int D, bool bf16, int
         default: return cudaErrorInvalidValue;
     }
 #undef B200T5_FWD_CASE
+#endif
 }
 
 }  // namespace b200t5

@@ -205,11 +205,9 @@ class FlashAttentionRPE(torch.autograd.Function):
 
 
 def fused_default() -> bool:
-    """Whether flash_attention_v2_rpe takes the in-kernel path when `fused` is not given.  B200T5_RPE_FUSED=0/1
-    overrides.  The in-kernel bias mode was written after this round's GPU budget was spent: it compiles for
-    sm_100a and its index arithmetic is checked on the CPU (tests/test_attention_rpe.py), but it has not run on
-    hardware yet, so the default stays on the composition of the validated kernels until it has."""
-    return os.environ.get("B200T5_RPE_FUSED", "0") == "1"
+    """Whether flash_attention_v2_rpe takes the in-kernel path when `fused` is not given: yes, unless
+    B200T5_RPE_FUSED=0 (developer switch for A/B runs against the composition of the dense kernels)."""
+    return os.environ.get("B200T5_RPE_FUSED", "1") != "0"
 
 
 def flash_attention_v2_rpe(q, k, v, rpe_weights, rpe_max_distance, causal=False, sm_scale=None,

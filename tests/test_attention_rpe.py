@@ -10,8 +10,8 @@ block, two 64-column halves, 32-column chunks), checked element by element again
 GPU (`-m gpu`): the public op against the same golden vectors and, bit for bit where the arithmetic is identical,
 against the dense-bias operator fed with the materialised bias.  Bars as in tests/test_attention_gpu.py
 (bf16: O, dV <= 4e-3, dQ, dK <= 1.2e-2 relative Frobenius); the table gradient inherits the dBias bar (1.2e-2).
-The in-kernel path has not run on hardware yet (GPU budget of the round was spent before it was written): its GPU
-tests are collected only with B200T5_RPE_FUSED=1, the composed path's tests always run.
+Both routes of the operator are tested: fused (bias computed in the attention kernels, the default) and composed
+(dense producer kernel + dense-bias kernels).
 """
 import ctypes as C
 import glob
@@ -240,7 +240,7 @@ def test_entry_points_validate_without_a_gpu(lib):
 # GPU
 # ------------------------------------------------------------------------------------------------------------
 TOL = {"o": 4e-3, "dv": 4e-3, "dq": 1.2e-2, "dk": 1.2e-2, "dtable": 1.2e-2}
-FUSED_MODES = [False] + ([True] if os.environ.get("B200T5_RPE_FUSED") == "1" else [])
+FUSED_MODES = [False, True]
 
 
 def _run_rpe(z, causal, scale, maxd, fused, dtype=torch.bfloat16):
@@ -266,7 +266,6 @@ def test_cuda_matches_reference_golden(path, fused):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("B200T5_RPE_FUSED") != "1", reason="in-kernel bias mode not yet validated on hardware")
 @pytest.mark.parametrize("shape", [(2, 4, 512, 512, 64, False), (2, 4, 512, 512, 64, True), (1, 2, 300, 700, 128, False),
                                    (2, 2, 640, 384, 32, True), (1, 3, 130, 130, 16, False), (3, 8, 1024, 1024, 64, False)],
                          ids=lambda s: "x".join(map(str, s)))
@@ -300,6 +299,6 @@ def test_cuda_library_launches_for_rpe():
     n0 = _cabi.launch_count()
     q = torch.randn(1, 2, 128, 64, device=DEV, dtype=torch.bfloat16)
     w = torch.randn(2, 32, device=DEV)
-    flash_attention_v2_rpe(q, q, q, w, 128, fused=False)
+    flash_attention_v2_rpe(q, q, q, w, 128)
     torch.cuda.synchronize()
-    assert _cabi.launch_count() >= n0 + 2                                     # producer + attention forward
+    assert _cabi.launch_count() == n0 + 2                                     # band + attention forward
