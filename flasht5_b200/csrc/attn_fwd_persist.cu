@@ -2,15 +2,23 @@
 //
 // Replaces /root/reference/src/model/ops/flash_attention_v2_bias.py:327-483 (`_fwd_kernel`).
 //
-// Same tile pipeline, warp roles, TMEM layout and arithmetic as attn_fwd.cu (the outputs are bit-identical); what
-// changes is the scheduling.  attn_fwd.cu launches one CTA per (batch, head, 128-row query block): a cycle-stamped
-// build (tools/fwd_timeline.py, profiles/r1e_fwd_timeline.txt) showed that of the ~38 k cycles such a CTA occupies
-// its half of an SM, ~3.3 k pass before the first score tile is ready (barrier init, TMEM allocation, the first Q/K
-// loads) and ~5 k between its last tile and the first stamp of the CTA that replaces it (epilogue, exit, launch) --
-// a fifth of the kernel.  Here the grid is 2 CTAs per SM (1 at D = 128) and every CTA walks work items
-// w = blockIdx.x, blockIdx.x + gridDim.x, ...: barriers and TMEM are set up once, the K/V ring and the bias ring run
-// ahead across work items, Q of the next item is loaded as soon as the last QK^T of the current one has retired, and
-// the first QK^T of the next item is issued while the softmax warps are still writing the current output.
+// Same tile pipeline, warp roles, TMEM layout and arithmetic as attn_fwd.cu (the outputs are bit-identical: checked on
+// B200 over 17 shapes / modes, profiles/r1e_fwd_persist_check.jsonl); what changes is the scheduling.  attn_fwd.cu
+// launches one CTA per (batch, head, 128-row query block): a cycle-stamped build (tools/fwd_timeline.py,
+// profiles/r1e_fwd_timeline_bias_2cta.txt) showed that of the ~37 k cycles such a CTA occupies its half of an SM,
+// ~3.3 k pass before the first score tile is ready (barrier init, TMEM allocation, the first Q/K loads) and ~5 k between
+// its last tile and the first stamp of the CTA that replaces it (epilogue, exit, launch).  Here the grid is 2 CTAs
+// per SM (1 at D = 128) and every CTA walks work items w = blockIdx.x, blockIdx.x + gridDim.x, ...: barriers and TMEM
+// are set up once, the K/V ring and the bias ring run ahead across work items, Q of the next item is loaded as soon
+// as the last QK^T of the current one has retired, and the first QK^T of the next item is issued while the softmax
+// warps are still writing the current output.  Two further changes in the softmax loop: the dense bias tile is pulled
+// into registers before the wait for S (its shared-memory reads, proxy fence and ring release leave the critical
+// path), and the row max is taken in the same straight-line block as the bias adds.
+//
+// MEASURED (B200, headline shape): 142.4 us against 142.8 us for attn_fwd.cu -- no gain, +2..7 % at S = 512 / D = 128,
+// -6 % at S = 4096 (static round-robin tail).  The schedule is therefore opt-in (B200T5_FWD_PERSIST=1) and the file is
+// kept as the starting point for the next round (first suspect: the two resident CTAs now start in lock-step, so
+// their MUFU-bound exp phases coincide instead of interleaving).
 //
 //   warp 4 (1 lane)  : TMA producer for Q (per work item) and the K / V ring (2 stages each)
 //   warp 6 (1 lane)  : TMA producer for the bias ring (2 stages of 128 rows x 64 columns)
