@@ -39,6 +39,9 @@ constexpr int kBM = 128;
 constexpr int kBN = 128;
 constexpr int kHalfBytes = 128 * 64 * 2;   // one [128][64] 16-bit swizzled half tile
 constexpr float kLog2e = 1.4426950408889634f;
+#ifndef B200T5_EXP2_POLY
+#define B200T5_EXP2_POLY 0      // developer switch, see attn_fwd.cu
+#endif
 
 template <int kD>
 struct Bwd2Cfg {
@@ -85,6 +88,27 @@ __device__ __forceinline__ void p_ds_chunk(const uint32_t (&sr)[32], const uint3
 #pragma unroll
     for (int c = 0; c < 32; c += 2) {
         float pe[2], de[2];
+#if B200T5_EXP2_POLY > 0
+        // developer build: of every 8 column pairs, B200T5_EXP2_POLY take the FMA-pipe exp2 (common.cuh).  P <= 1, so the
+        // argument never exceeds 0 by more than rounding; rows with L = -inf (no visible key) have a = -inf, which the
+        // polynomial clamps to 2^-125: they are zeroed explicitly, like masked columns.
+        const float a0 = fmaf(__uint_as_float(sr[c]), scale_log2, fmaf(bv[c], kLog2e, neg_L_log2));
+        const float a1 = fmaf(__uint_as_float(sr[c + 1]), scale_log2, fmaf(bv[c + 1], kLog2e, neg_L_log2));
+        if (((c / 2) % 8) < B200T5_EXP2_POLY) {
+            ex2_poly_pair(a0, a1, pe[0], pe[1]);
+            if (neg_L_log2 == -INFINITY) pe[0] = pe[1] = 0.f;
+        } else {
+            pe[0] = ex2_approx(a0);
+            pe[1] = ex2_approx(a1);
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            float e = pe[q];
+            if (kMask && (c + q >= lim)) e = 0.f;
+            pe[q] = e;
+            de[q] = e * (__uint_as_float(dr[c + q]) - dlt);
+        }
+#else
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             // exp2(S*scale*log2e + bias*log2e - L*log2e)
@@ -94,6 +118,7 @@ __device__ __forceinline__ void p_ds_chunk(const uint32_t (&sr)[32], const uint3
             pe[q] = e;
             de[q] = e * (__uint_as_float(dr[c + q]) - dlt);
         }
+#endif
         pp[c / 2] = pack2<kBf16>(pe[0], pe[1]);
         dd[c / 2] = pack2<kBf16>(de[0], de[1]);
     }

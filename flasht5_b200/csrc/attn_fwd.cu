@@ -36,6 +36,12 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kRescaleThreshold = 8.0f * kLn2;   // keep a stale max while exp(x - m) <= 256
 
+// Developer switch (A/B builds, tools/build_variant.sh): of every 8 column pairs, this many take their exp2 through the
+// FMA-pipe polynomial instead of the MUFU.  0 = product build.
+#ifndef B200T5_EXP2_POLY
+#define B200T5_EXP2_POLY 0
+#endif
+
 template <int kD>
 struct FwdSmem {
     static constexpr int kRowBytes = (kD >= 64 ? 64 : kD) * 2;   // bytes per smem row inside one swizzle box
@@ -433,8 +439,14 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdKernelParams p) {
             float s0 = 0.f, s1 = 0.f;
 #pragma unroll
             for (int c = 0; c < kBN; c += 2) {
-                const float e0 = ex2_approx(fmaf(x[c], kLog2e, neg_m_log2));
-                const float e1 = ex2_approx(fmaf(x[c + 1], kLog2e, neg_m_log2));
+                float e0, e1;
+                if (B200T5_EXP2_POLY > 0 && ((c / 2) % 8) < B200T5_EXP2_POLY) {
+                    // developer switch: this pair takes the FMA-pipe exp2 (common.cuh) instead of the MUFU
+                    ex2_poly_pair(fmaf(x[c], kLog2e, neg_m_log2), fmaf(x[c + 1], kLog2e, neg_m_log2), e0, e1);
+                } else {
+                    e0 = ex2_approx(fmaf(x[c], kLog2e, neg_m_log2));
+                    e1 = ex2_approx(fmaf(x[c + 1], kLog2e, neg_m_log2));
+                }
                 s0 += e0;
                 s1 += e1;
                 pk[c / 2] = pack2<kBf16>(e0, e1);
@@ -483,7 +495,12 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdKernelParams p) {
         if (num_tiles > 0) {
             mbar_wait(bars.pv_done, (num_tiles - 1) & 1);
             tc_fence_after();
+#if B200T5_EXP2_POLY > 0
+            // the polynomial clamps exp2(-inf) to 2^-125 instead of 0: a row with no visible key is recognised by its max
+            const float inv_l = (l_sum > 0.f && m_ref != -INFINITY) ? 1.f / l_sum : 0.f;
+#else
             const float inv_l = l_sum > 0.f ? 1.f / l_sum : 0.f;
+#endif
             constexpr int kChunk = kD >= 32 ? 32 : 16;
 #pragma unroll
             for (int c0 = 0; c0 < kD; c0 += kChunk) {

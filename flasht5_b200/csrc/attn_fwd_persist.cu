@@ -48,6 +48,9 @@ constexpr int kBiasHalfBytes = kBM * 64 * 2;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kRescaleThreshold = 8.0f * kLn2;   // keep a stale max while exp(x - m) <= 256
+#ifndef B200T5_EXP2_POLY
+#define B200T5_EXP2_POLY 0      // developer switch, see attn_fwd.cu
+#endif
 
 template <int kD>
 struct PFwdSmem {
@@ -463,8 +466,13 @@ attn_fwd_persist_kernel(const __grid_constant__ AttnFwdKernelParams p, const int
                 float s0 = 0.f, s1 = 0.f;
 #pragma unroll
                 for (int c = 0; c < kBN; c += 2) {
-                    const float e0 = ex2_approx(fmaf(x[c], kLog2e, neg_m_log2));
-                    const float e1 = ex2_approx(fmaf(x[c + 1], kLog2e, neg_m_log2));
+                    float e0, e1;
+                    if (B200T5_EXP2_POLY > 0 && ((c / 2) % 8) < B200T5_EXP2_POLY) {
+                        ex2_poly_pair(fmaf(x[c], kLog2e, neg_m_log2), fmaf(x[c + 1], kLog2e, neg_m_log2), e0, e1);
+                    } else {
+                        e0 = ex2_approx(fmaf(x[c], kLog2e, neg_m_log2));
+                        e1 = ex2_approx(fmaf(x[c + 1], kLog2e, neg_m_log2));
+                    }
                     s0 += e0;
                     s1 += e1;
                     pk[c / 2] = pack2<kBf16>(e0, e1);
@@ -511,7 +519,12 @@ attn_fwd_persist_kernel(const __grid_constant__ AttnFwdKernelParams p, const int
             if (num_tiles > 0) {
                 mbar_wait(bars.pv_done, (T - 1) & 1);
                 tc_fence_after();
+#if B200T5_EXP2_POLY > 0
+                // the polynomial clamps exp2(-inf) to 2^-125 instead of 0: a row with no visible key is recognised by its max
+                const float inv_l = (l_sum > 0.f && m_ref != -INFINITY) ? 1.f / l_sum : 0.f;
+#else
                 const float inv_l = l_sum > 0.f ? 1.f / l_sum : 0.f;
+#endif
                 constexpr int kChunk = kD >= 32 ? 32 : 16;
 #pragma unroll
                 for (int c0 = 0; c0 < kD; c0 += kChunk) {
