@@ -218,6 +218,15 @@ static bool fwd_persistent_enabled() {
     return v ? atoi(v) != 0 : kFwdPersistentDefault;
 }
 
+// Backward of the relative-position operator: B200T5_RPE_SKIP_CONST=1 lets tiles that lie entirely beyond a constant end
+// of the bucket table skip their dS store (their dS is summed in the kernel).  Built after this round's GPU budget was
+// spent: compiled and reviewed, not yet run on hardware, hence off by default.  Read on every call (A/B inside one process).
+constexpr bool kRpeSkipConstDefault = false;
+static bool rpe_skip_const_enabled() {
+    const char* v = getenv("B200T5_RPE_SKIP_CONST");
+    return v ? atoi(v) != 0 : kRpeSkipConstDefault;
+}
+
 // ---- in-kernel relative-position bias (bias mode 3) ----
 static int rpe_band_len(int const_lo, int const_hi) { return const_hi - const_lo + 2 * kRpeBandPad + 1; }
 
@@ -309,12 +318,12 @@ extern "C" int b200t5_attn_rpe_fwd(const b200t5_attn_params* p, const b200t5_rpe
 
 namespace {
 struct BwdWorkspace {
-    size_t delta_off, dq_off, ds_off, ds_bytes, dbias_off, total;
+    size_t delta_off, dq_off, ds_off, ds_bytes, dbias_off, dconst_off, total;
     int n_pad, ds_groups, ds_use_reduce, dq_groups;
 };
 // has_rpe: the bias is the in-kernel relative-position bias, i.e. a (1, H, M, N) bias whose dense gradient is only
 // an intermediate (kept in the workspace and folded into the (num_buckets, H) table gradient).
-BwdWorkspace bwd_workspace_layout(const b200t5_attn_params* p, bool has_rpe = false) {
+BwdWorkspace bwd_workspace_layout(const b200t5_attn_params* p, bool has_rpe = false, bool rpe_skip = false) {
     BwdWorkspace w;
     auto align = [](size_t x) { return (x + 255) / 256 * 256; };
     const size_t rows = (size_t)p->B * p->H * p->M;
@@ -335,7 +344,9 @@ BwdWorkspace bwd_workspace_layout(const b200t5_attn_params* p, bool has_rpe = fa
     w.ds_use_reduce = 0;
     size_t ds_bytes = 0;
     if (p->bias || has_rpe) {
-        if ((has_rpe || p->bias_B == 1) && p->B > 1) {
+        // (with the constant-tile skip of the relative-position path some tiles are never written: the surface must be
+        //  the zero-filled, reduce-added kind even for a single batch)
+        if (((has_rpe || p->bias_B == 1) && p->B > 1) || rpe_skip) {
             int g = (p->B + 7) / 8;
             if (g > 16) g = 16;
             w.ds_groups = g;
@@ -347,7 +358,8 @@ BwdWorkspace bwd_workspace_layout(const b200t5_attn_params* p, bool has_rpe = fa
     }
     w.ds_bytes = ds_bytes;
     w.dbias_off = w.ds_off + align(ds_bytes);
-    w.total = w.dbias_off + (has_rpe ? align((size_t)p->H * p->M * (size_t)p->N * 2) : 0);
+    w.dconst_off = w.dbias_off + (has_rpe ? align((size_t)p->H * p->M * (size_t)p->N * 2) : 0);
+    w.total = w.dconst_off + (has_rpe ? align((size_t)p->H * 2 * sizeof(float)) : 0);
     return w;
 }
 }  // namespace
@@ -359,7 +371,7 @@ extern "C" size_t b200t5_attn_bwd_workspace_bytes(const b200t5_attn_params* p) {
 
 extern "C" size_t b200t5_attn_rpe_bwd_workspace_bytes(const b200t5_attn_params* p, const b200t5_rpe_params* r) {
     if (!p || !r || p->B < 1 || p->H < 1 || p->M < 1 || p->N < 1 || p->D < 1) return 0;
-    return bwd_workspace_layout(p, true).total;
+    return bwd_workspace_layout(p, true, rpe_skip_const_enabled() && p->D <= 64).total;
 }
 
 static int attn_bwd_impl(const b200t5_attn_params* p, const b200t5_rpe_params* rpe) {
@@ -376,7 +388,8 @@ static int attn_bwd_impl(const b200t5_attn_params* p, const b200t5_rpe_params* r
     if (!strides_tma_ok(p->dout, p->do_strides, p->B, p->H) || !strides_tma_ok(p->dq, p->dq_strides, p->B, p->H) ||
         !strides_tma_ok(p->dk, p->dk_strides, p->B, p->H) || !strides_tma_ok(p->dv, p->dv_strides, p->B, p->H))
         return fail(B200T5_ERR_INVALID, "dout, dq, dk, dv need unit last stride, 16-byte aligned base and other strides that are multiples of 8 elements");
-    const BwdWorkspace w = bwd_workspace_layout(p, rpe != nullptr);
+    const bool rpe_skip = rpe != nullptr && rpe_skip_const_enabled() && p->D <= 64;   // the D = 128 kernel stores every tile
+    const BwdWorkspace w = bwd_workspace_layout(p, rpe != nullptr, rpe_skip);
     if (!p->workspace || p->workspace_bytes < w.total) return fail(B200T5_ERR_WORKSPACE, "workspace of %zu bytes needed, %zu given", w.total, p->workspace ? p->workspace_bytes : (size_t)0);
     if (reinterpret_cast<uintptr_t>(p->workspace) % 256 != 0) return fail(B200T5_ERR_WORKSPACE, "workspace must be 256-byte aligned");
     if ((rc = require_sm100(p->device))) return rc;
@@ -406,7 +419,16 @@ static int attn_bwd_impl(const b200t5_attn_params* p, const b200t5_rpe_params* r
     if ((rc = make_map_4d(&kp.map_dq, dq_ws, 2, dt, p->D, p->M, p->H, (uint64_t)w.dq_groups * p->B, p->D, (int64_t)p->M * p->D, (int64_t)p->H * p->M * p->D, boxd, 128, "dq group surface", true))) return rc;
     kp.dq_groups = w.dq_groups;
     const int mode = rpe ? 3 : bias_mode_of(p);
-    if (mode == 3) fill_rpe_band(&kp.rpe, rpe);
+    float* dconst = nullptr;
+    if (mode == 3) {
+        fill_rpe_band(&kp.rpe, rpe);
+        if (rpe_skip) {
+            dconst = reinterpret_cast<float*>(ws + w.dconst_off);
+            e = cudaMemsetAsync(dconst, 0, (size_t)p->H * 2 * sizeof(float), stream);
+            if (e != cudaSuccess) return fail_cuda(e, "cudaMemsetAsync(dconst)");
+            kp.rpe.dconst = dconst;
+        }
+    }
     if (mode == 1) {
         if ((rc = make_map_4d(&kp.map_bias, p->bias, 2, dt, p->N, p->M, p->bias_H, p->bias_B, p->bias_strides[2], p->bias_strides[1], p->bias_strides[0], 64, 128, "bias"))) return rc;
     } else if (mode == 2) {
@@ -450,6 +472,10 @@ static int attn_bwd_impl(const b200t5_attn_params* p, const b200t5_rpe_params* r
         e = launch_t5_bias_bwd(dbias_ws, rpe->lut, rpe->lut_zero, rpe->lut_len, nullptr, nullptr, rpe->dtable, p->H, p->M, p->N,
                                rpe->num_buckets, p->dtype, stream);
         if (e != cudaSuccess) return fail_cuda(e, "t5_bias_bwd launch");
+        if (dconst) {
+            e = launch_rpe_dtable_add_const(rpe->dtable, dconst, rpe->lut, rpe->lut_zero, rpe->lut_len, rpe->const_lo, rpe->const_hi, p->H, stream);
+            if (e != cudaSuccess) return fail_cuda(e, "rpe_dtable_add_const launch");
+        }
         return 0;
     }
     e = launch_attn_bwd_finalize(dq_ws, w.dq_groups, p->dq, p->dq_strides, p->B, p->H, p->M, p->N, p->D, p->sm_scale, bf16,

@@ -80,11 +80,13 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* r) {
 }
 
 // P and dS for 32 columns of one row.  sr / dr: S and dP accumulators (fp32 bits); bv: bias (already fp32);
-// outputs packed 16-bit pairs.  kMask: this tile crosses the causal diagonal or the key tail.
-template <bool kBf16, bool kMask>
+// outputs packed 16-bit pairs.  kMask: this tile crosses the causal diagonal or the key tail.  kSum: also add the
+// (unrounded) dS values of the chunk to ds_sum (bias mode 3, tiles whose bias is one constant: see the kernel).
+template <bool kBf16, bool kMask, bool kSum = false>
 __device__ __forceinline__ void p_ds_chunk(const uint32_t (&sr)[32], const uint32_t (&dr)[32], const float (&bv)[32],
                                            float scale_log2, float neg_L_log2, float dlt, int lim, uint32_t (&pp)[16],
-                                           uint32_t (&dd)[16]) {
+                                           uint32_t (&dd)[16], float* ds_sum = nullptr) {
+    float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
     for (int c = 0; c < 32; c += 2) {
         float pe[2], de[2];
@@ -121,7 +123,12 @@ __device__ __forceinline__ void p_ds_chunk(const uint32_t (&sr)[32], const uint3
 #endif
         pp[c / 2] = pack2<kBf16>(pe[0], pe[1]);
         dd[c / 2] = pack2<kBf16>(de[0], de[1]);
+        if constexpr (kSum) {
+            sum0 += de[0];
+            sum1 += de[1];
+        }
     }
+    if constexpr (kSum) *ds_sum += sum0 + sum1;
 }
 
 }  // namespace
@@ -394,6 +401,10 @@ attn_bwd_kernel_v2(const __grid_constant__ AttnBwdKernelParams p) {
             for (int i = ctid; i < p.rpe.band_len; i += 256) dst[i] = __ldg(src + i);
             named_bar_sync(3, 256);
         }
+        // bias mode 3 with p.rpe.dconst: tiles entirely beyond a constant end of the bucket table send no dS tile to the
+        // surface; their dS is summed here (fp32) and leaves the CTA as two numbers (one per side)
+        const bool rpe_skip = kBiasMode == 3 && p.rpe.dconst != nullptr;
+        float ds_const_lo = 0.f, ds_const_hi = 0.f;
 
         // row statistics are prefetched one block ahead (global latency off the critical path)
         float L_next = 0.f, dlt_next = 0.f;
@@ -482,7 +493,13 @@ attn_bwd_kernel_v2(const __grid_constant__ AttnBwdKernelParams p) {
 #pragma unroll
                     for (int e = 0; e < 32; ++e) bv[e] = 0.f;
                 }
-                if (need_mask)
+                if (kBiasMode == 3 && rpe_skip && rpe_const) {
+                    float* acc = (col0 - mrow0 + (kBN - 1) <= p.rpe.const_lo) ? &ds_const_lo : &ds_const_hi;
+                    if (need_mask)
+                        p_ds_chunk<kBf16, true, true>(sr, dr, bv, scale_log2, neg_L_log2, dlt, lim - ch * 32, pp[ch], dd[ch], acc);
+                    else
+                        p_ds_chunk<kBf16, false, true>(sr, dr, bv, scale_log2, neg_L_log2, dlt, 0, pp[ch], dd[ch], acc);
+                } else if (need_mask)
                     p_ds_chunk<kBf16, true>(sr, dr, bv, scale_log2, neg_L_log2, dlt, lim - ch * 32, pp[ch], dd[ch]);
                 else
                     p_ds_chunk<kBf16, false>(sr, dr, bv, scale_log2, neg_L_log2, dlt, 0, pp[ch], dd[ch]);
@@ -535,7 +552,7 @@ attn_bwd_kernel_v2(const __grid_constant__ AttnBwdKernelParams p) {
             if (ctid == 0) BWD_TS(0, k, 7);
             if (ctid == 0) {
                 mbar_arrive(pds_full);
-                if (kBiasMode != 0) {
+                if (kBiasMode != 0 && !(kBiasMode == 3 && rpe_skip && rpe_const)) {
                     if (p.ds_use_reduce) {
                         tma_reduce_add_4d(&p.map_ds, smem + C::kDS, col0, mrow0, h, g);
                         tma_reduce_add_4d(&p.map_ds, smem + C::kDS + kHalfBytes, col0 + 64, mrow0, h, g);
@@ -557,6 +574,28 @@ attn_bwd_kernel_v2(const __grid_constant__ AttnBwdKernelParams p) {
             fence_proxy_async_smem();
             named_bar_sync(2, 256);
             if (ctid == 0) issue_dq_reduce((n_iter - 1) & 1, (i_start + n_iter - 1) * kBM);
+        }
+        if (kBiasMode == 3 && rpe_skip) {
+            // 256 threads x 2 sums -> 8 warps x 2 -> 2 atomics per CTA.  The band's shared memory is free again: every
+            // thread has left the loop when it reaches the barrier (barrier 2 above when n_iter > 0, the first one below).
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                ds_const_lo += __shfl_xor_sync(0xffffffffu, ds_const_lo, off);
+                ds_const_hi += __shfl_xor_sync(0xffffffffu, ds_const_hi, off);
+            }
+            float* red = reinterpret_cast<float*>(smem + C::kBias);
+            named_bar_sync(3, 256);
+            if (lane == 0) {
+                red[(ctid >> 5) * 2 + 0] = ds_const_lo;
+                red[(ctid >> 5) * 2 + 1] = ds_const_hi;
+            }
+            named_bar_sync(3, 256);
+            if (ctid < 2) {
+                float t = 0.f;
+#pragma unroll
+                for (int w8 = 0; w8 < 8; ++w8) t += red[w8 * 2 + ctid];
+                if (t != 0.f) atomicAdd(p.rpe.dconst + h * 2 + ctid, t);
+            }
         }
         {
             const int gn = col0 + r;

@@ -17,6 +17,9 @@ struct RpeBand {
     const float* band;      // (H, band_len) fp32
     int band_lo, band_len;
     int const_lo, const_hi;
+    // backward, optional: tiles that lie entirely beyond a constant end do not store dS; the CTA adds the sum of its
+    // dS over such tiles to dconst[h * 2 + side] (side 0: rel <= const_lo, 1: rel >= const_hi), fp32, pre-zeroed
+    float* dconst;          // NULL: every tile stores dS
 };
 constexpr int kRpeBandPad = 255;        // 2 * 128 - 1 relative positions per tile
 constexpr int kRpeMaxBandLen = 8192;    // 32 KB of shared memory (the dense bias ring's space)
@@ -126,6 +129,10 @@ cudaError_t launch_t5_bias_bwd(const void* dbias, const int32_t* lut, int lut_ze
 cudaError_t launch_rpe_band(const void* table, int64_t stride_b, int64_t stride_h, int table_dtype, const int32_t* lut,
                             int lut_zero, int lut_len, float* band, int H, int band_lo, int band_len, int io_dtype,
                             cudaStream_t stream);
+
+// dtable[lut[const_lo + lut_zero], h] += dconst[h][0];  dtable[lut[const_hi + lut_zero], h] += dconst[h][1]
+cudaError_t launch_rpe_dtable_add_const(float* dtable, const float* dconst, const int32_t* lut, int lut_zero, int lut_len,
+                                        int const_lo, int const_hi, int H, cudaStream_t stream);
 
 // Launch counter (every kernel launched by this library bumps it; read through the C ABI).
 void count_launch(int n = 1);

@@ -345,6 +345,28 @@ cudaError_t launch_rpe_band(const void* table, int64_t stride_b, int64_t stride_
     return cudaGetLastError();
 }
 
+__global__ void rpe_dtable_add_const_kernel(float* __restrict__ dtable, const float* __restrict__ dconst,
+                                            const int32_t* __restrict__ lut, int lut_zero, int lut_len, int const_lo,
+                                            int const_hi, int H) {
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= H) return;
+    int i0 = const_lo + lut_zero, i1 = const_hi + lut_zero;
+    i0 = i0 < 0 ? 0 : (i0 >= lut_len ? lut_len - 1 : i0);
+    i1 = i1 < 0 ? 0 : (i1 >= lut_len ? lut_len - 1 : i1);
+    const int b0 = __ldg(lut + i0), b1 = __ldg(lut + i1);
+    // one thread per head; the two buckets may coincide (a table with a single bucket): add one after the other
+    dtable[(int64_t)b0 * H + h] += dconst[h * 2 + 0];
+    dtable[(int64_t)b1 * H + h] += dconst[h * 2 + 1];
+}
+
+cudaError_t launch_rpe_dtable_add_const(float* dtable, const float* dconst, const int32_t* lut, int lut_zero, int lut_len,
+                                        int const_lo, int const_hi, int H, cudaStream_t stream) {
+    rpe_dtable_add_const_kernel<<<(H + 127) / 128, 128, 0, stream>>>(dtable, dconst, lut, lut_zero, lut_len, const_lo,
+                                                                    const_hi, H);
+    count_launch();
+    return cudaGetLastError();
+}
+
 cudaError_t launch_t5_bias_bwd(const void* dbias, const int32_t* lut, int lut_zero, int lut_len, const int32_t* ctx_pos,
                                const int32_t* mem_pos, float* dtable, int H, int M, int N, int num_buckets, int dbias_dtype,
                                cudaStream_t stream) {

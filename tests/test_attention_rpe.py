@@ -294,6 +294,49 @@ def test_cuda_fused_equals_dense_operator(shape):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(2, 4, 512, 512, 64, False), (2, 2, 640, 384, 16, True)], ids=lambda s: "x".join(map(str, s)))
+def test_cuda_constant_tile_skip(shape):
+    """B200T5_RPE_SKIP_CONST=1 (developer switch, off by default): tiles entirely beyond a constant end of the bucket
+    table keep their dS in the kernel instead of storing it.  dQ/dK/dV must not change; the table gradient is compared
+    with the fp64 oracle on the scale of the |dS| mass that flows into each bucket (the second shape is the degenerate
+    one: every visible position falls into ONE bucket, whose exact gradient is 0 because rows of dS sum to zero)."""
+    from flasht5_b200 import flash_attention_v2_rpe
+    B, H, M, N, D, causal = shape
+    g = torch.Generator().manual_seed(11)
+    mk = lambda s: torch.randn(B, s, H, D, generator=g).to(torch.bfloat16).permute(0, 2, 1, 3)   # noqa: E731
+    q, k, v, do = mk(M), mk(N), mk(N), mk(M)
+    w = 0.5 * torch.randn(H, 32, generator=g)
+    outs = {}
+    old = os.environ.get("B200T5_RPE_SKIP_CONST")
+    try:
+        for skip in ("0", "1"):
+            os.environ["B200T5_RPE_SKIP_CONST"] = skip
+            qq, kk, vv, ww = (t.to(DEV).requires_grad_(True) for t in (q, k, v, w))
+            o = flash_attention_v2_rpe(qq, kk, vv, ww, 128, causal=causal, sm_scale=1.0, fused=True)
+            outs[skip] = (o,) + torch.autograd.grad(o, (qq, kk, vv, ww), do.to(DEV))
+            torch.cuda.synchronize()
+    finally:
+        if old is None:
+            os.environ.pop("B200T5_RPE_SKIP_CONST", None)
+        else:
+            os.environ["B200T5_RPE_SKIP_CONST"] = old
+    for i, name in enumerate(("o", "dq", "dk", "dv")):
+        a, b = outs["0"][i], outs["1"][i]
+        if name == "dq":
+            assert orc.error_metrics(b, a.double())[1] < 4e-3
+        else:
+            assert torch.equal(a, b), name
+    table = w.t().contiguous()
+    bias = orc.t5_bias(table, M, N, bidirectional=not causal).to(torch.bfloat16).float()
+    ref = orc.attn_fwd_bwd(q.float(), k.float(), v.float(), bias, do.float(), causal, 1.0)
+    dt_ref = orc.t5_dtable(ref[5], M, N, not causal)
+    mass = orc.t5_dtable(ref[5].abs(), M, N, not causal)                       # |dS| flowing into each bucket
+    for skip in ("0", "1"):
+        err = (outs[skip][4].t().double().cpu() - dt_ref).norm() / mass.norm()
+        assert err < 4e-3, (skip, float(err))
+
+
+@pytest.mark.gpu
 def test_cuda_library_launches_for_rpe():
     from flasht5_b200 import flash_attention_v2_rpe
     n0 = _cabi.launch_count()
