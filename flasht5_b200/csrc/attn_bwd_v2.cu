@@ -692,12 +692,17 @@ static cudaError_t launch_bwd2_d(const AttnBwdKernelParams& kp, int bias_mode, b
 
 cudaError_t launch_attn_bwd_v2(const AttnBwdKernelParams& kp, int D, bool bf16, int bias_mode, bool causal,
                                cudaStream_t stream) {
+#ifdef B200T5_HEADLINE_ONLY
+    if (D == 64 && bf16) return launch_bwd2_d<64, true>(kp, bias_mode, causal, stream);
+    return cudaErrorInvalidValue;
+#else
     switch (D) {
         case 16: return bf16 ? launch_bwd2_d<16, true>(kp, bias_mode, causal, stream) : launch_bwd2_d<16, false>(kp, bias_mode, causal, stream);
         case 32: return bf16 ? launch_bwd2_d<32, true>(kp, bias_mode, causal, stream) : launch_bwd2_d<32, false>(kp, bias_mode, causal, stream);
         case 64: return bf16 ? launch_bwd2_d<64, true>(kp, bias_mode, causal, stream) : launch_bwd2_d<64, false>(kp, bias_mode, causal, stream);
         default: return cudaErrorInvalidValue;
     }
+#endif
 }
 
 }  // namespace b200t5

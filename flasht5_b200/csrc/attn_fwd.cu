@@ -637,6 +637,10 @@ cudaError_t launch_attn_fwd(const AttnFwdKernelParams& kp, int D, bool bf16, int
         if (bias_mode == 3) return launch_fwd_inst<64, true, 3, false>(kp, stream);
     }
     return cudaErrorInvalidValue;
+#elif defined(B200T5_HEADLINE_ONLY)
+    // developer variant libraries (tools/build_variant.sh --headline): D = 64, bf16 only -- a fifth of the compile time
+    if (D == 64 && bf16) return launch_fwd_d<64, true>(kp, bias_mode, causal, stream);
+    return cudaErrorInvalidValue;
 #else
 #define B200T5_FWD_CASE(DD)                                                              \
     case DD:                                                                             \

@@ -114,6 +114,34 @@ __device__ __forceinline__ WorkItem decode_work(int w, const AttnFwdKernelParams
 
 }  // namespace
 
+// Developer build (-DB200T5_FWD_TIMING, as in attn_fwd.cu): the CTAs resident on SM `kPTimedSm` stamp clock64 at the phase
+// boundaries of softmax thread 0 and of the MMA warp for their first kPTimedTiles score tiles (work-item boundaries show
+// up as the gap between "P stored" of one tile and "wait S" of the next); the launcher prints the timeline.
+#ifdef B200T5_FWD_TIMING
+constexpr int kPTimedSm = 17;
+constexpr int kPTimedTiles = 28;
+__device__ int g_pfwd_ts_slots;
+__device__ long long g_pfwd_ts[4][2][kPTimedTiles][8];   // [slot][role][tile][stamp]
+__device__ int g_pfwd_ts_bid[4];
+__device__ __forceinline__ long long pclk64() {
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+    return t;
+}
+#define PFWD_TS(role, t_, slot_)                                                                       \
+    do {                                                                                               \
+        if (ts_slot >= 0 && (t_) < (uint32_t)kPTimedTiles) g_pfwd_ts[ts_slot][role][t_][slot_] = pclk64(); \
+    } while (0)
+#else
+#define PFWD_TS(role, t_, slot_) do { } while (0)
+#endif
+
+// Developer switch: the CTAs of the second half of the grid (the second CTA of every SM) start their softmax this many
+// nanoseconds late, so that the two resident CTAs' MUFU-bound exp phases do not begin in lock-step.  0 = off.
+#ifndef B200T5_PERSIST_STAGGER_NS
+#define B200T5_PERSIST_STAGGER_NS 0
+#endif
+
 template <int kD, bool kBf16, int kBiasMode, bool kCausal>
 __global__ void __launch_bounds__(256, 2)   // 128 regs at launch; setmaxnreg re-splits them per role
 attn_fwd_persist_kernel(const __grid_constant__ AttnFwdKernelParams p, const int total_work) {
@@ -176,6 +204,26 @@ attn_fwd_persist_kernel(const __grid_constant__ AttnFwdKernelParams p, const int
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+#ifdef B200T5_FWD_TIMING
+    int ts_slot = -1;
+    {
+        volatile int& s_ts_slot = *reinterpret_cast<volatile int*>(smem + L::kTmemSlot + 8);   // spare word, no static smem
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        if (threadIdx.x == 0) {
+            s_ts_slot = -1;
+            if (smid == kPTimedSm) {
+                const int sl = atomicAdd(&g_pfwd_ts_slots, 1);
+                if (sl < 4) {
+                    s_ts_slot = sl;
+                    g_pfwd_ts_bid[sl] = blockIdx.x;
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 || (warp == 5 && lane == 0)) ts_slot = s_ts_slot;
+    }
+#endif
 
     if (warp >= 4) {
         // =============================== control warps ===============================
@@ -267,19 +315,24 @@ attn_fwd_persist_kernel(const __grid_constant__ AttnFwdKernelParams p, const int
                 mbar_wait(bars.k_full + (T % kKVStages), (T / kKVStages) & 1);
                 if (T > 0) mbar_wait(bars.s_empty, (T - 1) & 1);
                 tc_fence_after();
+                PFWD_TS(1, T, 0);
                 issue_s(T, it.num_tiles == 1);
+                PFWD_TS(1, T, 1);
                 for (int j = 0; j < it.num_tiles; ++j, ++T) {
                     if (j + 1 < it.num_tiles) {
                         const uint32_t tn = T + 1;
                         mbar_wait(bars.k_full + (tn % kKVStages), (tn / kKVStages) & 1);
                         mbar_wait(bars.s_empty, T & 1);
                         tc_fence_after();
+                        PFWD_TS(1, tn, 0);
                         issue_s(tn, j + 2 == it.num_tiles);
+                        PFWD_TS(1, tn, 1);
                     }
                     const int s = T % kKVStages;
                     mbar_wait(bars.v_full + s, (T / kKVStages) & 1);
                     mbar_wait(bars.p_full, T & 1);      // (j == 0: also means the previous item's O has been read)
                     tc_fence_after();
+                    PFWD_TS(1, T, 2);
                     const uint32_t v_lo = v_lo0 + s * (L::kTileBytes >> 4);
                     if (leader) {
 #pragma unroll
@@ -292,6 +345,7 @@ attn_fwd_persist_kernel(const __grid_constant__ AttnFwdKernelParams p, const int
                         umma_commit(bars.v_empty + s);
                     }
                     __syncwarp();
+                    PFWD_TS(1, T, 3);
                 }
                 ++W;
             }
@@ -309,6 +363,7 @@ attn_fwd_persist_kernel(const __grid_constant__ AttnFwdKernelParams p, const int
 
         uint32_t T = 0;       // score tiles so far
         uint32_t I = 0;       // bias halves so far
+        if (B200T5_PERSIST_STAGGER_NS > 0 && blockIdx.x >= gridDim.x / 2) __nanosleep(B200T5_PERSIST_STAGGER_NS);
         for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
             const WorkItem it = decode_work<kCausal>(w, p);
             const int b = it.b, h = it.h, row0 = it.row0, num_tiles = it.num_tiles;
@@ -339,6 +394,7 @@ attn_fwd_persist_kernel(const __grid_constant__ AttnFwdKernelParams p, const int
 
                 // ---- dense bias tile -> registers (packed 16-bit pairs) before the scores are needed: the shared-memory
                 //      reads, the proxy fence and the release of the ring overlap the wait for S ----
+                PFWD_TS(0, T, 0);
                 uint32_t bw[kBN / 2];
                 if (kBiasMode == 1) {
 #pragma unroll
@@ -368,6 +424,7 @@ attn_fwd_persist_kernel(const __grid_constant__ AttnFwdKernelParams p, const int
 
                 mbar_wait(bars.s_full, T & 1);
                 tc_fence_after();
+                PFWD_TS(0, T, 1);
                 {
                     uint32_t(&xr)[kBN] = reinterpret_cast<uint32_t(&)[kBN]>(x);
                     tmem_ld32(tm_s + 0, reinterpret_cast<uint32_t(&)[32]>(xr[0]));
@@ -379,6 +436,7 @@ attn_fwd_persist_kernel(const __grid_constant__ AttnFwdKernelParams p, const int
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bars.s_empty);
+                PFWD_TS(0, T, 2);
 
                 // ---- scores = S * sm_scale + bias, and their row max.  The max is taken in the same straight-line
                 //      block as the adds (its dependent chain hides inside them); a tile that needs masking (the
@@ -453,6 +511,8 @@ attn_fwd_persist_kernel(const __grid_constant__ AttnFwdKernelParams p, const int
                     }
                 }
 
+                PFWD_TS(0, T, 3);
+                PFWD_TS(0, T, 3);                                 // scores + bias + row max done
                 // ---- online softmax with lazy rescale ----
                 float alpha = 1.f;
                 if (tmax > m_ref + kRescaleThreshold) {       // also true for the first finite tile (m_ref = -inf)
@@ -478,6 +538,7 @@ attn_fwd_persist_kernel(const __grid_constant__ AttnFwdKernelParams p, const int
                     pk[c / 2] = pack2<kBf16>(e0, e1);
                 }
                 l_sum = l_sum * alpha + (s0 + s1);
+                PFWD_TS(0, T, 5);
 
                 if (j > 0) {
                     mbar_wait(bars.pv_done, (T - 1) & 1);     // O and the P buffer are free again
@@ -504,12 +565,14 @@ attn_fwd_persist_kernel(const __grid_constant__ AttnFwdKernelParams p, const int
                     }
                 }
                 // (j == 0: the P buffer is free -- the epilogue of the previous item waited for its last P V)
+                PFWD_TS(0, T, 6);
                 tmem_st32(tm_p + 0, reinterpret_cast<const uint32_t(&)[32]>(pk[0]));
                 tmem_st32(tm_p + 32, reinterpret_cast<const uint32_t(&)[32]>(pk[32]));
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bars.p_full);
+                PFWD_TS(0, T, 7);
             }
 
             // ---- epilogue: O / l -> global (row-contiguous 16-byte stores), LSE ----
@@ -583,8 +646,42 @@ static cudaError_t launch_pfwd_inst(const AttnFwdKernelParams& kp, cudaStream_t 
     const long long total = (long long)kp.B * kp.H * kp.num_m_blocks;
     const long long slots = (long long)num_sms * L::kCtasPerSm;
     const int grid = static_cast<int>(total < slots ? total : slots);
+#ifdef B200T5_FWD_TIMING
+    {
+        int zero = 0;
+        cudaMemcpyToSymbol(g_pfwd_ts_slots, &zero, sizeof(int));
+    }
+#endif
     kern<<<grid, 256, L::kTotal, stream>>>(kp, static_cast<int>(total));
     count_launch();
+#ifdef B200T5_FWD_TIMING
+    {
+        cudaDeviceSynchronize();
+        static long long ts[4][2][kPTimedTiles][8];
+        int bids[4], n = 0;
+        cudaMemcpyFromSymbol(ts, g_pfwd_ts, sizeof(ts));
+        cudaMemcpyFromSymbol(bids, g_pfwd_ts_bid, sizeof(bids));
+        cudaMemcpyFromSymbol(&n, g_pfwd_ts_slots, sizeof(int));
+        if (n > 4) n = 4;
+        long long t0 = n > 0 ? ts[0][0][0][0] : 0;
+        for (int s = 0; s < n; ++s)
+            if (ts[s][0][0][0] < t0) t0 = ts[s][0][0][0];
+        printf("PFWD_TIMING sm %d: %d resident CTAs (grid %d); softmax thread 0 per score tile: [tile start, S ready, S in regs, "
+               "bias+max done, -, exp done, P V(t-1) done, P stored]; mma: [S(t) issue start, S(t) issued, P(t) ready, PV(t) issued]\n",
+               kPTimedSm, n, grid);
+        for (int s = 0; s < n; ++s) {
+            printf(" CTA slot %d (block %d)\n", s, bids[s]);
+            for (int j = 0; j < kPTimedTiles; ++j) {
+                printf("  t=%d sm:", j);
+                for (int q = 0; q < 8; ++q) printf(" %7lld", q == 4 ? 0LL : ts[s][0][j][q] - t0);
+                printf("   mma:");
+                for (int q = 0; q < 4; ++q) printf(" %7lld", ts[s][1][j][q] - t0);
+                printf("\n");
+            }
+        }
+        fflush(stdout);
+    }
+#endif
     return cudaGetLastError();
 }
 
@@ -605,6 +702,10 @@ static cudaError_t launch_pfwd_d(const AttnFwdKernelParams& kp, int bias_mode, b
 
 cudaError_t launch_attn_fwd_persist(const AttnFwdKernelParams& kp, int D, bool bf16, int bias_mode, bool causal,
                                     cudaStream_t stream) {
+#ifdef B200T5_HEADLINE_ONLY
+    if (D == 64 && bf16) return launch_pfwd_d<64, true>(kp, bias_mode, causal, stream);
+    return cudaErrorInvalidValue;
+#else
 #define B200T5_PFWD_CASE(DD)                                                             \
     case DD:                                                                             \
         return bf16 ? launch_pfwd_d<DD, true>(kp, bias_mode, causal, stream)             \
@@ -617,6 +718,7 @@ cudaError_t launch_attn_fwd_persist(const AttnFwdKernelParams& kp, int D, bool b
         default: return cudaErrorInvalidValue;
     }
 #undef B200T5_PFWD_CASE
+#endif
 }
 
 }  // namespace b200t5
