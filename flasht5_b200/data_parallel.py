@@ -12,7 +12,7 @@ from typing import Optional, Tuple
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_batch", "allreduce_dbias", "allreduce_dbias_overlapped"]
+__all__ = ["shard_batch", "allreduce_dbias", "allreduce_dbias_overlapped", "allreduce_dtable"]
 
 
 def shard_batch(global_batch: int, rank: int, world_size: int) -> Tuple[int, int]:
@@ -50,3 +50,10 @@ def allreduce_dbias_overlapped(dbias: Optional[torch.Tensor], comm_stream: "torc
         out = acc.to(dbias.dtype)
     dbias.record_stream(comm_stream)
     return out
+
+
+def allreduce_dtable(dtable: Optional[torch.Tensor], group=None) -> Optional[torch.Tensor]:
+    """The exchange of the in-kernel relative-position operator (flash_attention_v2_rpe): its only shared gradient is
+    the (num_buckets, H) table gradient -- 1 KB instead of the 33.5 MB dBias of the dense operator at the headline
+    shape -- summed over ranks in fp32.  (Inside a DDP-wrapped model this is simply the embedding weight's bucket.)"""
+    return allreduce_dbias(dtable, group)

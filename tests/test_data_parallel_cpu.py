@@ -26,7 +26,7 @@ def _worker(rank, world, port, tmp):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from flasht5_b200.data_parallel import allreduce_dbias, shard_batch
+    from flasht5_b200.data_parallel import allreduce_dbias, allreduce_dtable, shard_batch
     from oracle import attn_bias_ref as orc
     torch.manual_seed(0)                                   # same global problem on every rank
     B, H, M, N, D = 5, 2, 24, 40, 16
@@ -45,6 +45,15 @@ def _worker(rank, world, port, tmp):
     db64 = loc[5].clone()
     dist.all_reduce(db64)
     ok &= torch.allclose(db64, full[5], atol=1e-12)
+    # the relative-position operator: bias from a (32, H) table, the one shared gradient is the table's
+    table = torch.randn(32, H, dtype=torch.float64)
+    full_r = orc.attn_rpe_fwd_bwd(q, k, v, table, do, True, 0.5)
+    loc_r = orc.attn_rpe_fwd_bwd(q[a:b], k[a:b], v[a:b], table, do[a:b], True, 0.5)
+    for i in (0, 2, 3, 4):
+        ok &= torch.allclose(loc_r[i], full_r[i][a:b], atol=1e-12)
+    dt = allreduce_dtable(loc_r[5].float())
+    ok &= dt.dtype == torch.float32 and dt.shape == (32, H)
+    ok &= torch.allclose(dt.double(), full_r[5], atol=1e-4, rtol=1e-5)
     with open(os.path.join(tmp, f"ok{rank}"), "w") as f:
         f.write("1" if ok else "0")
     dist.destroy_process_group()
