@@ -41,6 +41,10 @@ constexpr float kRescaleThreshold = 8.0f * kLn2;   // keep a stale max while exp
 #ifndef B200T5_EXP2_POLY
 #define B200T5_EXP2_POLY 0
 #endif
+// Developer switch: with sm_scale == 1 the dense bias is added with the mixed-precision add (common.cuh: add_f32_16x2).
+#ifndef B200T5_BIAS_FHADD
+#define B200T5_BIAS_FHADD 0
+#endif
 
 template <int kD>
 struct FwdSmem {
@@ -355,6 +359,21 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdKernelParams p) {
                     const int s = it % kBiasStages;
                     mbar_wait(bars.b_full + s, (it / kBiasStages) & 1);
                     const uint8_t* brow = smem + L::kBias + s * kBiasHalfBytes + r * 128;
+#if B200T5_BIAS_FHADD
+                    if (p.sm_scale == 1.f) {
+                        // developer build: bias add straight from the packed 16-bit pair (one FHADD per element)
+#pragma unroll
+                        for (int c8 = 0; c8 < 8; ++c8) {
+                            const uint4 u = *reinterpret_cast<const uint4*>(brow + ((c8 ^ (r & 7)) << 4));
+                            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int c = hh * 64 + c8 * 8 + e * 2;
+                                add_f32_16x2<kBf16>(w[e], x[c], x[c + 1], x[c], x[c + 1]);
+                            }
+                        }
+                    } else
+#endif
 #pragma unroll
                     for (int c8 = 0; c8 < 8; ++c8) {
                         const uint4 u = *reinterpret_cast<const uint4*>(brow + ((c8 ^ (r & 7)) << 4));

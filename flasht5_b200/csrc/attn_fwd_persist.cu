@@ -51,6 +51,9 @@ constexpr float kRescaleThreshold = 8.0f * kLn2;   // keep a stale max while exp
 #ifndef B200T5_EXP2_POLY
 #define B200T5_EXP2_POLY 0      // developer switch, see attn_fwd.cu
 #endif
+#ifndef B200T5_BIAS_FHADD
+#define B200T5_BIAS_FHADD 0     // developer switch, see attn_fwd.cu
+#endif
 
 template <int kD>
 struct PFwdSmem {
@@ -458,6 +461,13 @@ attn_fwd_persist_kernel(const __grid_constant__ AttnFwdKernelParams p, const int
                 };
                 float tmax;
                 if (kBiasMode == 1) {
+#if B200T5_BIAS_FHADD
+                    if (p.sm_scale == 1.f) {
+                        // developer build: bias add straight from the packed 16-bit pair (one FHADD per element)
+#pragma unroll
+                        for (int c = 0; c < kBN; c += 2) add_f32_16x2<kBf16>(bw[c / 2], x[c], x[c + 1], x[c], x[c + 1]);
+                    } else
+#endif
 #pragma unroll
                     for (int c = 0; c < kBN; c += 2) {
                         const float2 f = unpack2<kBf16>(bw[c / 2]);

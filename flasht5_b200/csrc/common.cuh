@@ -472,6 +472,22 @@ __device__ __forceinline__ float to_float16bit(uint16_t u) {
     }
 }
 
+// fp32 + one 16-bit half of a packed register in ONE instruction (sm_100 mixed-precision add, SASS FHADD.BF16 / .F16):
+// the dense-bias add without the separate unpack when sm_scale == 1 (x * 1 + b and x + b round identically).
+// Measured 109 / clk / SM (profiles/r1e_pipe_bench.txt).  Used by the B200T5_BIAS_FHADD developer builds.
+template <bool kBf16>
+__device__ __forceinline__ void add_f32_16x2(uint32_t packed, float c_lo, float c_hi, float& d_lo, float& d_hi) {
+    if constexpr (kBf16) {
+        asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tadd.rn.f32.bf16 %0, lo, %3;\n\tadd.rn.f32.bf16 %1, hi, %4;\n\t}"
+            : "=f"(d_lo), "=f"(d_hi)
+            : "r"(packed), "f"(c_lo), "f"(c_hi));
+    } else {
+        asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tadd.rn.f32.f16 %0, lo, %3;\n\tadd.rn.f32.f16 %1, hi, %4;\n\t}"
+            : "=f"(d_lo), "=f"(d_hi)
+            : "r"(packed), "f"(c_lo), "f"(c_hi));
+    }
+}
+
 // byte offset of element (row, col) inside a [rows][64 x 16-bit] tile written with the 128B swizzle
 // (Swizzle<3,4,3>: 16-byte chunk index ^= row % 8).  Tile base must be 1024-byte aligned.
 __device__ __forceinline__ uint32_t swz128_offset(int row, int col16b /* element index 0..63 */) {
