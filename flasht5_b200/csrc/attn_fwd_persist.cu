@@ -646,13 +646,11 @@ static cudaError_t launch_pfwd_inst(const AttnFwdKernelParams& kp, cudaStream_t 
     auto kern = attn_fwd_persist_kernel<kD, kBf16, kBiasMode, kCausal>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     if (e != cudaSuccess) return e;
-    static int num_sms = 0;                       // one device kind per process (sm_100a only): cache the SM count
-    if (num_sms == 0) {
-        int dev = 0, n = 0;
-        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
-        if ((e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-        num_sms = n;
-    }
+    // SM count of the current device (the C ABI has made the caller's device current); queried per launch: the call costs
+    // well under a microsecond and keeps the launcher stateless across devices and threads
+    int dev = 0, num_sms = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     const long long total = (long long)kp.B * kp.H * kp.num_m_blocks;
     const long long slots = (long long)num_sms * L::kCtasPerSm;
     const int grid = static_cast<int>(total < slots ? total : slots);
