@@ -13,6 +13,7 @@ from .rms_norm import Fast_RMS_Layernorm, fast_rms_layernorm
 from .cross_entropy_loss import CrossEntropyLoss, cross_entropy_loss
 from .positional_encoding import RelativePositionalEncoding
 from .flash_attention_rpe import FlashAttentionRPE, flash_attention_v2_rpe
+from .adamw_scaled import AdamWScale
 
 __all__ = [
     "flash_attention_v2_bias", "FlashAttentionAdditiveBias",
@@ -20,5 +21,6 @@ __all__ = [
     "cross_entropy_loss", "CrossEntropyLoss",
     "RelativePositionalEncoding",
     "flash_attention_v2_rpe", "FlashAttentionRPE",
+    "AdamWScale",
 ]
 __version__ = "0.1.0"

@@ -53,6 +53,15 @@ class RpeParams(C.Structure):
     ]
 
 
+class AdamwTensor(C.Structure):
+    """Mirror of `b200t5_adamw_tensor` (include/b200t5.h)."""
+    _fields_ = [
+        ("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("comp", C.c_void_p),
+        ("numel", C.c_int64), ("first_chunk", C.c_int32), ("sqrt_numel", C.c_float), ("ss_base", C.c_float),
+        ("ss_floor", C.c_float), ("neg_lr_wd", C.c_float), ("reserved", C.c_int32),
+    ]
+
+
 # every symbol include/b200t5.h declares: name -> (restype, argtypes)
 _i64, _i32, _f, _vp, _sz = C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_size_t
 SYMBOLS = {
@@ -73,6 +82,9 @@ SYMBOLS = {
     "b200t5_attn_rpe_fwd": (_i32, [C.POINTER(AttnParams), C.POINTER(RpeParams)]),
     "b200t5_attn_rpe_bwd_workspace_bytes": (_sz, [C.POINTER(AttnParams), C.POINTER(RpeParams)]),
     "b200t5_attn_rpe_bwd": (_i32, [C.POINTER(AttnParams), C.POINTER(RpeParams)]),
+    "b200t5_adamw_chunk_elems": (_i32, []),
+    "b200t5_adamw_workspace_bytes": (_sz, [_i32, _i32]),
+    "b200t5_adamw_scale_step": (_i32, [_vp, _i32, _vp, _i32, _vp, _sz, _i32, _i32, _i32, _f, _f, _f, _i32, _i32, _vp]),
     "b200t5_abi_version": (_i32, []),
     "b200t5_last_error": (C.c_char_p, []),
     "b200t5_launch_count": (C.c_uint64, []),

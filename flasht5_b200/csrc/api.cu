@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstddef>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -627,6 +628,47 @@ extern "C" int b200t5_t5_bias_bwd(const void* dbias, const int32_t* lut, int32_t
     if (guard.err != cudaSuccess) return fail_cuda(guard.err, "cudaSetDevice");
     cudaError_t e = launch_t5_bias_bwd(dbias, lut, lut_zero, lut_len, ctx_pos, mem_pos, dtable, H, M, N, num_buckets, dbias_dtype, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return fail_cuda(e, "t5_bias_bwd launch");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// fused multi-tensor AdamWScale step
+// ------------------------------------------------------------------------------------------
+static_assert(sizeof(b200t5_adamw_tensor) == sizeof(AdamwTensor) && offsetof(b200t5_adamw_tensor, neg_lr_wd) == offsetof(AdamwTensor, neg_lr_wd) &&
+              offsetof(b200t5_adamw_tensor, numel) == offsetof(AdamwTensor, numel), "AdamwTensor must mirror b200t5_adamw_tensor");
+
+extern "C" int b200t5_adamw_chunk_elems(void) { return adamw_chunk_elems(); }
+
+extern "C" size_t b200t5_adamw_workspace_bytes(int32_t n_tensors, int32_t n_chunks) {
+    if (n_tensors < 0 || n_chunks < 0) return 0;
+    auto align = [](size_t x) { return (x + 255) / 256 * 256; };
+    return align((size_t)n_chunks * sizeof(float)) + align((size_t)n_tensors * sizeof(float));
+}
+
+extern "C" int b200t5_adamw_scale_step(const b200t5_adamw_tensor* tensors, int32_t n_tensors, const int32_t* chunk_tensor,
+                                       int32_t n_chunks, void* workspace, size_t workspace_bytes, int p_dtype,
+                                       int state_dtype, int kahan, float beta1, float beta2, float eps,
+                                       int round_step_to_p, int device, void* stream) {
+    if (n_tensors < 0 || n_chunks < 0) return fail(B200T5_ERR_INVALID, "negative tensor / chunk count");
+    if (n_tensors == 0 || n_chunks == 0) return 0;
+    if (!tensors || !chunk_tensor) return fail(B200T5_ERR_INVALID, "tensors and chunk_tensor must be non-NULL");
+    int rc;
+    if ((rc = check_dtype3(p_dtype, "parameter")) || (rc = check_dtype3(state_dtype, "state"))) return rc;
+    if (kahan && p_dtype == B200T5_F32) return fail(B200T5_ERR_INVALID, "Kahan compensation applies to 16-bit parameters only (reference :107-111)");
+    if (p_dtype != B200T5_F32 && state_dtype != p_dtype) return fail(B200T5_ERR_UNSUPPORTED, "16-bit parameters keep their states in the parameter dtype");
+    if (!(beta1 >= 0.f && beta1 < 1.f) || !(beta2 >= 0.f && beta2 < 1.f) || !(eps >= 0.f)) return fail(B200T5_ERR_INVALID, "betas must be in [0, 1) and eps >= 0");
+    const size_t need = b200t5_adamw_workspace_bytes(n_tensors, n_chunks);
+    if (!workspace || workspace_bytes < need) return fail(B200T5_ERR_WORKSPACE, "workspace of %zu bytes needed", need);
+    if (reinterpret_cast<uintptr_t>(workspace) % 256 != 0) return fail(B200T5_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+    if ((rc = require_sm100(device))) return rc;
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return fail_cuda(guard.err, "cudaSetDevice");
+    float* chunk_sumsq = static_cast<float*>(workspace);
+    float* neg_step = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + ((size_t)n_chunks * sizeof(float) + 255) / 256 * 256);
+    cudaError_t e = launch_adamw_step(reinterpret_cast<const AdamwTensor*>(tensors), n_tensors, chunk_tensor, n_chunks, chunk_sumsq,
+                                      neg_step, p_dtype, state_dtype, kahan != 0, beta1, beta2, eps, round_step_to_p != 0,
+                                      static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail_cuda(e, "adamw_step launch");
     return 0;
 }
 

@@ -134,6 +134,27 @@ cudaError_t launch_rpe_band(const void* table, int64_t stride_b, int64_t stride_
 cudaError_t launch_rpe_dtable_add_const(float* dtable, const float* dconst, const int32_t* lut, int lut_zero, int lut_len,
                                         int const_lo, int const_hi, int H, cudaStream_t stream);
 
+// Fused multi-tensor AdamWScale step (adamw.cu).  One descriptor per parameter tensor (device array); mirrors
+// b200t5_adamw_tensor of the public header (checked with a static_assert in api.cu).
+struct AdamwTensor {
+    void* p;
+    const void* g;
+    void* m;
+    void* v;
+    void* comp;             // Kahan compensation, NULL unless enabled
+    int64_t numel;
+    int32_t first_chunk;    // index of the tensor's first chunk in the launch
+    float sqrt_numel;       // (float)(numel ** 0.5)
+    float ss_base;          // step size before the rms factor
+    float ss_floor;         // step size when rms(p) <= 1e-3
+    float neg_lr_wd;        // -(lr * weight_decay); 0 = no decay
+    int32_t reserved;
+};
+int adamw_chunk_elems();
+cudaError_t launch_adamw_step(const AdamwTensor* tensors, int n_tensors, const int32_t* chunk_tensor, int n_chunks,
+                              float* chunk_sumsq, float* neg_step, int p_dtype, int state_dtype, bool kahan, float beta1,
+                              float beta2, float eps, bool round_step_to_p, cudaStream_t stream);
+
 // Launch counter (every kernel launched by this library bumps it; read through the C ABI).
 void count_launch(int n = 1);
 

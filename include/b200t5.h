@@ -182,6 +182,44 @@ B200T5_API size_t b200t5_attn_rpe_bwd_workspace_bytes(const b200t5_attn_params* 
 B200T5_API int b200t5_attn_rpe_bwd(const b200t5_attn_params* p, const b200t5_rpe_params* r);
 
 /* ------------------------------------------------------------------------------------------------
+ * Fused multi-tensor AdamWScale step.
+ * Replaces AdamWScale._adamwscaled / _foreach_adamwscaled, src/utils/adamw_scaled.py:154-211, :213-281: Adam moments,
+ * step size x max(1e-3, rms(parameter)), optional Kahan compensation for 16-bit parameters, decoupled weight decay --
+ * three launches for all tensors of a (parameter dtype, state dtype, kahan) group, no host synchronisation.
+ * `tensors`: DEVICE array of n_tensors descriptors; `chunk_tensor`: DEVICE int32[n_chunks], the tensor every
+ * b200t5_adamw_chunk_elems()-element chunk belongs to (chunks of a tensor are consecutive, first_chunk is its first).
+ * The caller computes, with the reference's own expressions (:173-180),
+ *   ss_base  = lr [* sqrt(1 - beta2^t) / (1 - beta1^t)]      as fp32
+ *   ss_floor = that step size x 1e-3                          (used when rms(p) <= 1e-3)
+ *   round_step_to_p: 1 when the step size x rms product is a tensor of the parameter dtype in the reference (no bias
+ *                    correction: python float x 16-bit rms tensor), 0 when it is fp32 (bias correction on).
+ * p_dtype / state_dtype: B200T5_F16 | B200T5_BF16 | B200T5_F32; state_dtype == p_dtype, or 16-bit states under fp32
+ * parameters (use_state_dtype); kahan requires a 16-bit p_dtype.  Gradients have the parameter dtype.
+ * workspace: b200t5_adamw_workspace_bytes(n_tensors, n_chunks) bytes, 256-byte aligned.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct b200t5_adamw_tensor {
+    void* p;
+    const void* g;
+    void* m;
+    void* v;
+    void* comp;             /* Kahan compensation (parameter dtype), NULL unless kahan */
+    int64_t numel;
+    int32_t first_chunk;
+    float sqrt_numel;       /* (float)(numel ** 0.5) */
+    float ss_base;
+    float ss_floor;
+    float neg_lr_wd;        /* -(lr * weight_decay) as fp32; 0 = no decay */
+    int32_t reserved;
+} b200t5_adamw_tensor;
+
+B200T5_API int b200t5_adamw_chunk_elems(void);
+B200T5_API size_t b200t5_adamw_workspace_bytes(int32_t n_tensors, int32_t n_chunks);
+B200T5_API int b200t5_adamw_scale_step(const b200t5_adamw_tensor* tensors, int32_t n_tensors, const int32_t* chunk_tensor,
+                                       int32_t n_chunks, void* workspace, size_t workspace_bytes, int p_dtype,
+                                       int state_dtype, int kahan, float beta1, float beta2, float eps,
+                                       int round_step_to_p, int device, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Library state
  * ---------------------------------------------------------------------------------------------- */
 B200T5_API int b200t5_abi_version(void);

@@ -27,8 +27,9 @@ sys.dont_write_bytecode = True
 from src.utils.attn_ref import attn_ref                                  # noqa: E402  (reference)
 from src.model.modeling_flash_t5 import FlashT5LayerNorm, FlashT5CrossEntropyLoss  # noqa: E402
 from src.utils.positional_encoding import RelativePositionalEncoding     # noqa: E402
+from src.utils.adamw_scaled import AdamWScale                            # noqa: E402
 
-from oracle import attn_bias_ref, rmsnorm_ref, ce_ref                    # noqa: E402
+from oracle import attn_bias_ref, rmsnorm_ref, ce_ref, adamw_ref         # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden")
 os.makedirs(GOLD, exist_ok=True)
@@ -242,12 +243,80 @@ def gen_attn_rpe():
         print(f"rpe_{name}: ok  (oracle==reference)")
 
 
+# name: (dtype, kahan, foreach, weight_decay, correct_bias, shapes)
+ADAMW_CASES = {
+    "fp32_wd": (torch.float32, False, False, 0.03, True, [(300, 7), (513,), (4, 5, 6)]),
+    "fp32_foreach_nobc": (torch.float32, False, True, 0.0, False, [(300, 7), (64,)]),
+    "bf16_kahan_wd": (torch.bfloat16, True, False, 0.03, True, [(300, 7), (513,), (8, 16)]),
+    "bf16_plain": (torch.bfloat16, False, False, 0.0, True, [(300, 7), (33,)]),
+    "bf16_kahan_foreach": (torch.bfloat16, True, True, 0.01, True, [(129, 3), (40,)]),
+    "fp32_tiny_rms": (torch.float32, False, False, 0.0, True, [(50, 4)]),          # rms(p) < 1e-3: the 1e-3 floor applies
+}
+
+
+def gen_adamw():
+    """Three steps of the REFERENCE optimizer (CPU) on seeded parameters / gradients; the oracle's dtype-faithful
+    restatement must reproduce the per-tensor path bit for bit and stay within rounding of the foreach path."""
+    lr, betas, eps = 2e-2, (0.9, 0.95), 1e-6
+    for i, (name, (dt, kahan, foreach, wd, cb, shapes)) in enumerate(ADAMW_CASES.items()):
+        rng = np.random.default_rng(500 + i)
+        scale = 1e-4 if name == "fp32_tiny_rms" else 1.0
+        p0 = [torch.from_numpy((scale * rng.standard_normal(s)).astype(np.float32)).to(dt) for s in shapes]
+        grads = [[torch.from_numpy(rng.standard_normal(s).astype(np.float32)).to(dt) for s in shapes] for _ in range(3)]
+        params = [torch.nn.Parameter(t.clone()) for t in p0]
+        opt = AdamWScale(params, lr=lr, betas=betas, eps=eps, weight_decay=wd, kahan_sum=kahan, foreach=foreach, correct_bias=cb)
+        # the oracle, stepped alongside
+        om = [torch.zeros_like(t) for t in p0]
+        ov = [torch.zeros_like(t) for t in p0]
+        oc = [torch.zeros_like(t) if (kahan and dt != torch.float32) else None for t in p0]
+        op = [t.clone() for t in p0]
+        for step in range(3):
+            for prm, g in zip(params, grads[step]):
+                prm.grad = g.clone()
+            opt.step()
+            for j in range(len(op)):
+                op[j], om[j], ov[j], oc[j] = adamw_ref.step_like_reference(op[j], grads[step][j], om[j], ov[j], oc[j], step + 1, lr,
+                                                                            betas[0], betas[1], eps, wd, cb)
+        out = {"dtype": np.array(str(dt)), "kahan": np.array(kahan), "foreach": np.array(foreach), "weight_decay": np.array(wd),
+               "correct_bias": np.array(cb), "lr": np.array(lr), "beta1": np.array(betas[0]), "beta2": np.array(betas[1]),
+               "eps": np.array(eps), "n": np.array(len(shapes))}
+        for j, prm in enumerate(params):
+            st = opt.state[prm]
+            ref = (prm.detach(), st["exp_avg"], st["exp_avg_sq"], st["kahan_comp"])
+            mine = (op[j], om[j], ov[j], oc[j])
+            for nm, a, b_ in zip(("p", "m", "v", "comp"), mine, ref):
+                if b_ is None:
+                    assert a is None, (name, nm)
+                    continue
+                if not foreach:
+                    assert torch.equal(a, b_), (name, j, nm, (a.float() - b_.float()).abs().max())
+                else:                      # regrouped arithmetic: within a few roundings of the tensor dtype
+                    tol = 2e-2 if dt == torch.bfloat16 else 1e-5
+                    if nm == "comp":       # the compensation term is a rounding residual: compare the compensated value p + c
+                        a, b_cmp = mine[0].float() + a.float(), ref[0].float() + b_.float()
+                        tol = 2e-3
+                    else:
+                        b_cmp = b_.float()
+                    err = (a.float() - b_cmp).abs().max().item()
+                    assert err <= tol * b_cmp.abs().max().item() + 1e-12, (name, j, nm, err)
+                out[f"{nm}{j}"] = b_.float().numpy()
+            out[f"p0_{j}"] = p0[j].float().numpy()
+            for step in range(3):
+                out[f"g{step}_{j}"] = grads[step][j].float().numpy()
+        np.savez_compressed(os.path.join(GOLD, f"adamw_{name}.npz"), **out)
+        print(f"adamw_{name}: ok  (oracle==reference)")
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
+    if "--only-adamw" in sys.argv:
+        gen_adamw()
+        sys.exit(0)
     if "--only-rpe" in sys.argv:
         gen_attn_rpe()
         sys.exit(0)
     gen_attn_rpe()
+    gen_adamw()
     gen_t5_bias()
     gen_buckets()
     gen_attn()

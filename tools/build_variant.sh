@@ -21,5 +21,5 @@ for f in $FILES; do
 done
 wait
 nvcc -shared -o $ROOT/flasht5_b200/libb200t5_$NAME.so $OUT/attn_fwd.o $OUT/attn_fwd_persist.o $OUT/attn_bwd.o $OUT/attn_bwd_v2.o \
-  $BASE/norm_ce.o $BASE/t5_bias.o $BASE/api.o -gencode arch=compute_100a,code=sm_100a -cudart static
+  $BASE/norm_ce.o $BASE/t5_bias.o $BASE/adamw.o $BASE/api.o -gencode arch=compute_100a,code=sm_100a -cudart static
 ls -la $ROOT/flasht5_b200/libb200t5_$NAME.so
