@@ -222,11 +222,14 @@ static bool fwd_persistent_enabled() {
 // Backward of the relative-position operator: B200T5_RPE_SKIP_CONST=1 lets tiles that lie entirely beyond a constant end
 // of the bucket table skip their dS store (their dS is summed in the kernel).  Built after this round's GPU budget was
 // spent: compiled and reviewed, not yet run on hardware, hence off by default.  Read on every call (A/B inside one process).
-constexpr bool kRpeSkipConstDefault = false;
-static bool rpe_skip_const_enabled() {
+constexpr int kRpeSkipConstDefault = 0;
+// 0: every tile stores dS.  1: constant tiles keep dS in the kernel (validated on B200, untimed).  2: as 1, and the table
+// gradient is reduced straight from the non-constant tiles of the dS surface (rpe_dtable_band_kernel; not yet run).
+static int rpe_skip_const_level() {
     const char* v = getenv("B200T5_RPE_SKIP_CONST");
-    return v ? atoi(v) != 0 : kRpeSkipConstDefault;
+    return v ? atoi(v) : kRpeSkipConstDefault;
 }
+static bool rpe_skip_const_enabled() { return rpe_skip_const_level() != 0; }
 
 // ---- in-kernel relative-position bias (bias mode 3) ----
 static int rpe_band_len(int const_lo, int const_hi) { return const_hi - const_lo + 2 * kRpeBandPad + 1; }
@@ -461,6 +464,17 @@ static int attn_bwd_impl(const b200t5_attn_params* p, const b200t5_rpe_params* r
     }
     if (e != cudaSuccess) return fail_cuda(e, "attn_bwd launch");
 
+    if (rpe && dconst && rpe_skip_const_level() >= 2) {
+        // developer path: dQ conversion alone, then the table gradient straight from the non-constant tiles of the surface
+        e = launch_attn_bwd_dq_convert(dq_ws, w.dq_groups, p->dq, p->dq_strides, p->B, p->H, p->M, p->D, p->sm_scale, bf16, stream);
+        if (e != cudaSuccess) return fail_cuda(e, "attn_bwd_dq_convert launch");
+        e = launch_rpe_dtable_band(ds_ws, w.n_pad, w.ds_groups > 0 ? w.ds_groups : 1, p->H, p->M, p->N, rpe->lut, rpe->lut_zero, rpe->lut_len,
+                                   rpe->const_lo, rpe->const_hi, rpe->dtable, rpe->num_buckets, p->causal != 0, bf16, stream);
+        if (e != cudaSuccess) return fail_cuda(e, "rpe_dtable_band launch");
+        e = launch_rpe_dtable_add_const(rpe->dtable, dconst, rpe->lut, rpe->lut_zero, rpe->lut_len, rpe->const_lo, rpe->const_hi, p->H, stream);
+        if (e != cudaSuccess) return fail_cuda(e, "rpe_dtable_add_const launch");
+        return 0;
+    }
     if (rpe) {
         // dense (1, H, M, N) gradient into the workspace (sum over the batch groups), then the producer's segmented
         // sum folds it into the (num_buckets, H) table gradient

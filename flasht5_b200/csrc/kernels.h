@@ -130,6 +130,10 @@ cudaError_t launch_rpe_band(const void* table, int64_t stride_b, int64_t stride_
                             int lut_zero, int lut_len, float* band, int H, int band_lo, int band_len, int io_dtype,
                             cudaStream_t stream);
 
+// (developer path) table gradient straight from the non-constant tiles of the dS group surface; zeroes dtable first
+cudaError_t launch_rpe_dtable_band(const void* ds_ws, int pitch, int G, int H, int M, int N, const int32_t* lut, int lut_zero,
+                                   int lut_len, int const_lo, int const_hi, float* dtable, int num_buckets, bool causal,
+                                   bool bf16, cudaStream_t stream);
 // dtable[lut[const_lo + lut_zero], h] += dconst[h][0];  dtable[lut[const_hi + lut_zero], h] += dconst[h][1]
 cudaError_t launch_rpe_dtable_add_const(float* dtable, const float* dconst, const int32_t* lut, int lut_zero, int lut_len,
                                         int const_lo, int const_hi, int H, cudaStream_t stream);

@@ -345,6 +345,83 @@ cudaError_t launch_rpe_band(const void* table, int64_t stride_b, int64_t stride_
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------
+// Table gradient of the in-kernel relative-position bias straight from the 16-bit dS group surface (developer path,
+// B200T5_RPE_SKIP_CONST=2): only the tiles that are NOT entirely beyond a constant end of the bucket table carry
+// data (the attention backward keeps the others' dS in registers), so only those are read -- 3 of 8 tiles per query
+// block at S = 1024 -- and neither the dense (1,H,M,N) dBias scratch nor the producer's segmented sum is needed.
+// One CTA = one (key block, query block, head, group slice).  Thread t walks the wrapped diagonal w = t % 128 of its half of
+// the rows: lanes read consecutive 16-bit elements; a wrapped diagonal is two true diagonals (d = w and d = w - 128).
+// ------------------------------------------------------------------------------------------
+template <bool kBf16>
+__global__ void __launch_bounds__(256) rpe_dtable_band_kernel(const uint16_t* __restrict__ ws, int pitch, int G, int H, int M,
+                                                              int N, const int32_t* __restrict__ lut, int lut_zero,
+                                                              int lut_len, int const_lo, int const_hi,
+                                                              float* __restrict__ dtable, int num_buckets, int causal) {
+    const int col0 = blockIdx.x * 128, row0 = blockIdx.y * 128;
+    const int h = blockIdx.z / G, g = blockIdx.z % G;
+    const int rel_min = col0 - row0 - 127, rel_max = col0 - row0 + 127;
+    if (rel_max <= const_lo || rel_min >= const_hi) return;        // constant tile: summed inside the attention kernel
+    if (causal && col0 > row0 + 127 + (N - M)) return;             // entirely masked: never written, reads as zero
+    __shared__ float sdiag[256];                                    // index d + 128, d = c - r in [-127, 127]
+    __shared__ float sbucket[kMaxBuckets];
+    sdiag[threadIdx.x] = 0.f;
+    for (int i = threadIdx.x; i < num_buckets; i += 256) sbucket[i] = 0.f;
+    __syncthreads();
+    const int w = threadIdx.x & 127, half = threadIdx.x >> 7;
+    const uint16_t* base = ws + ((int64_t)g * H + h) * (int64_t)M * pitch;
+    float s_pos = 0.f, s_neg = 0.f;
+#pragma unroll 8
+    for (int rr = 0; rr < 64; ++rr) {
+        const int r = half * 64 + rr;
+        const int m = row0 + r;
+        int c = r + w;
+        const bool wrapped = c >= 128;
+        c &= 127;
+        const int n = col0 + c;
+        if (m < M && n < N) {
+            const float v = to_float16bit<kBf16>(__ldg(base + (int64_t)m * pitch + n));
+            if (wrapped) s_neg += v;
+            else s_pos += v;
+        }
+    }
+    atomicAdd(&sdiag[w + 128], s_pos);          // two adders per slot (the two halves of the rows)
+    atomicAdd(&sdiag[w], s_neg);                // d = w - 128 (slot 0 = d -128: no elements, stays 0)
+    __syncthreads();
+    {
+        const int d = static_cast<int>(threadIdx.x) - 128;
+        const float v = sdiag[threadIdx.x];
+        if (v != 0.f) {
+            int idx = col0 - row0 + d + lut_zero;
+            idx = idx < 0 ? 0 : (idx >= lut_len ? lut_len - 1 : idx);
+            atomicAdd(&sbucket[__ldg(lut + idx)], v);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < num_buckets; i += 256) {
+        const float v = sbucket[i];
+        if (v != 0.f) atomicAdd(dtable + (int64_t)i * H + h, v);
+    }
+}
+
+cudaError_t launch_rpe_dtable_band(const void* ds_ws, int pitch, int G, int H, int M, int N, const int32_t* lut, int lut_zero,
+                                   int lut_len, int const_lo, int const_hi, float* dtable, int num_buckets, bool causal,
+                                   bool bf16, cudaStream_t stream) {
+    if (num_buckets > kMaxBuckets) return cudaErrorInvalidValue;
+    cudaError_t e = cudaMemsetAsync(dtable, 0, (size_t)num_buckets * H * sizeof(float), stream);
+    if (e != cudaSuccess) return e;
+    const dim3 grid((N + 127) / 128, (M + 127) / 128, H * G);
+    if (grid.y > 65535 || grid.z > 65535) return cudaErrorInvalidValue;
+    if (bf16)
+        rpe_dtable_band_kernel<true><<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(ds_ws), pitch, G, H, M, N, lut, lut_zero,
+                                                               lut_len, const_lo, const_hi, dtable, num_buckets, causal ? 1 : 0);
+    else
+        rpe_dtable_band_kernel<false><<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(ds_ws), pitch, G, H, M, N, lut, lut_zero,
+                                                                lut_len, const_lo, const_hi, dtable, num_buckets, causal ? 1 : 0);
+    count_launch();
+    return cudaGetLastError();
+}
+
 __global__ void rpe_dtable_add_const_kernel(float* __restrict__ dtable, const float* __restrict__ dconst,
                                             const int32_t* __restrict__ lut, int lut_zero, int lut_len, int const_lo,
                                             int const_hi, int H) {
