@@ -1,5 +1,5 @@
 """Developer tool (GPU box): the fused AdamWScale step against the HBM roof and against the reference's own code paths.
-A FAT5-small-like parameter set (147 M parameters in ~200 tensors) is stepped with
+A FAT5-small-like parameter set (about 110 M parameters in 258 tensors) is stepped with
   * flasht5_b200.AdamWScale (three launches per dtype group), and
   * an inline restatement of the reference's foreach arithmetic with torch._foreach ops (the reference module itself is not
     on the box), as the "what it replaces" number.
