@@ -218,6 +218,11 @@ static bool fwd_persistent_enabled() {
     const char* v = getenv("B200T5_FWD_PERSIST");
     return v ? atoi(v) != 0 : kFwdPersistentDefault;
 }
+// B200T5_FWD_PINGPONG=1: the two-query-tile forward (attn_fwd_pingpong.cu; developer kernel, not yet run on hardware)
+static bool fwd_pingpong_enabled() {
+    const char* v = getenv("B200T5_FWD_PINGPONG");
+    return v && atoi(v) != 0;
+}
 
 // Backward of the relative-position operator: B200T5_RPE_SKIP_CONST=1 lets tiles that lie entirely beyond a constant end
 // of the bucket table skip their dS store (their dS is summed in the kernel).  Built after this round's GPU budget was
@@ -307,6 +312,9 @@ static int attn_fwd_impl(const b200t5_attn_params* p, const b200t5_rpe_params* r
         ProfScope prof(B200T5_KERNEL_ATTN_FWD, static_cast<cudaStream_t>(p->stream));
         // the persistent schedule covers the TMA / in-kernel bias modes; the pointer path (mode 2) keeps one CTA per block
         const bool persist = fwd_persistent_enabled() && mode != 2;
+        if (fwd_pingpong_enabled() && mode != 2 && p->D <= 64)
+            e = launch_attn_fwd_pingpong(kp, p->D, p->dtype == B200T5_BF16, mode, p->causal != 0, static_cast<cudaStream_t>(p->stream));
+        else
         e = persist ? launch_attn_fwd_persist(kp, p->D, p->dtype == B200T5_BF16, mode, p->causal != 0, static_cast<cudaStream_t>(p->stream))
                     : launch_attn_fwd(kp, p->D, p->dtype == B200T5_BF16, mode, p->causal != 0, static_cast<cudaStream_t>(p->stream));
     }

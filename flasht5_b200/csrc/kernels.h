@@ -77,6 +77,9 @@ cudaError_t launch_attn_fwd(const AttnFwdKernelParams& kp, int D, bool bf16, int
 // persistent schedule of the same forward (attn_fwd_persist.cu): 2 CTAs per SM walk the work items
 cudaError_t launch_attn_fwd_persist(const AttnFwdKernelParams& kp, int D, bool bf16, int bias_mode, bool causal,
                                     cudaStream_t stream);
+// developer kernel (attn_fwd_pingpong.cu): two query tiles per CTA, exp phases in anti-phase; D <= 64, bias modes 0, 1, 3
+cudaError_t launch_attn_fwd_pingpong(const AttnFwdKernelParams& kp, int D, bool bf16, int bias_mode, bool causal,
+                                     cudaStream_t stream);
 cudaError_t launch_attn_bwd(const AttnBwdKernelParams& kp, int D, bool bf16, int bias_mode, bool causal,
                             cudaStream_t stream);        // dispatches: D <= 64 -> pipelined v2 kernel, D = 128 -> v1
 cudaError_t launch_attn_bwd_v2(const AttnBwdKernelParams& kp, int D, bool bf16, int bias_mode, bool causal,

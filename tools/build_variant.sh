@@ -14,12 +14,12 @@ SRC=$ROOT/flasht5_b200/csrc; OUT=$ROOT/flasht5_b200/build/$NAME; BASE=$ROOT/flas
 [ -f $BASE/api.o ] || python -m flasht5_b200.build > /dev/null
 mkdir -p $OUT
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr"
-FILES="attn_fwd attn_fwd_persist attn_bwd_v2"
+FILES="attn_fwd attn_fwd_persist attn_fwd_pingpong attn_bwd_v2"
 if [ $HEADLINE == 1 ]; then EXTRA="$EXTRA -DB200T5_HEADLINE_ONLY"; cp $BASE/attn_bwd.o $OUT/attn_bwd.o; else FILES="$FILES attn_bwd"; fi
 for f in $FILES; do
   nvcc $FLAGS $EXTRA -c $SRC/$f.cu -o $OUT/$f.o &
 done
 wait
-nvcc -shared -o $ROOT/flasht5_b200/libb200t5_$NAME.so $OUT/attn_fwd.o $OUT/attn_fwd_persist.o $OUT/attn_bwd.o $OUT/attn_bwd_v2.o \
+nvcc -shared -o $ROOT/flasht5_b200/libb200t5_$NAME.so $OUT/attn_fwd.o $OUT/attn_fwd_persist.o $OUT/attn_fwd_pingpong.o $OUT/attn_bwd.o $OUT/attn_bwd_v2.o \
   $BASE/norm_ce.o $BASE/t5_bias.o $BASE/adamw.o $BASE/api.o -gencode arch=compute_100a,code=sm_100a -cudart static
 ls -la $ROOT/flasht5_b200/libb200t5_$NAME.so

@@ -1,5 +1,6 @@
-"""Developer tool (GPU box): the persistent forward schedule (attn_fwd_persist.cu) against the one-CTA-per-block kernel
-(attn_fwd.cu): outputs must be bit-identical (same arithmetic, different scheduling); then time both.
+"""Developer tool (GPU box): the persistent forward schedule (attn_fwd_persist.cu) and the two-query-tile forward
+(attn_fwd_pingpong.cu) against the one-CTA-per-block kernel (attn_fwd.cu): outputs must be bit-identical (same arithmetic,
+different scheduling); then time all three.
 Results are appended to gpurun_out/persist_check.jsonl as they come.   usage: python tools/fwd_persist_check.py"""
 import json
 import os
@@ -27,8 +28,10 @@ from flasht5_b200 import flash_attention_rpe as rpe   # noqa: E402
 DEV = "cuda:0"
 
 
-def fwd(mode_persist, q, k, v, bias, causal, scale, band=None, lo=0, hi=0):
-    os.environ["B200T5_FWD_PERSIST"] = "1" if mode_persist else "0"
+def fwd(mode, q, k, v, bias, causal, scale, band=None, lo=0, hi=0):
+    """mode: False / "base" = attn_fwd.cu, True / "persist" = attn_fwd_persist.cu, "pingpong" = attn_fwd_pingpong.cu"""
+    os.environ["B200T5_FWD_PERSIST"] = "1" if mode in (True, "persist") else "0"
+    os.environ["B200T5_FWD_PINGPONG"] = "1" if mode == "pingpong" else "0"
     if band is not None:
         return torch.ops.b200t5.attn_rpe_fwd(q, k, v, band, lo, hi, causal, scale)
     return torch.ops.b200t5.attn_bias_fwd(q, k, v, bias, causal, scale)
@@ -66,14 +69,19 @@ def make(case):
 
 
 all_ok = True
+all_ok_pp = True
 for case in CASES:
     try:
         q, k, v, bias, band, lo, hi = make(case)
         o0, L0 = fwd(False, q, k, v, bias, case[6], 1.0, band, lo, hi)
         o1, L1 = fwd(True, q, k, v, bias, case[6], 1.0, band, lo, hi)
         o2, L2 = fwd(True, q, k, v, bias, case[6], 1.0, band, lo, hi)      # and once more: run-to-run determinism
+        o3, L3 = fwd("pingpong", q, k, v, bias, case[6], 1.0, band, lo, hi)
         torch.cuda.synchronize()
         ok = bool(torch.equal(o0, o1) and torch.equal(L0, L1) and torch.equal(o1, o2) and torch.equal(L1, L2))
+        ok_pp = bool(torch.equal(o0, o3) and torch.equal(L0, L3))
+        log(step="equal_pingpong", case=[str(c) for c in case], ok=ok_pp, maxdiff=float((o0.float() - o3.float()).abs().max()))
+        all_ok_pp &= ok_pp
         fin = bool(torch.isfinite(o1.float()).all())
         all_ok &= ok and fin
         log(step="equal", case=[str(c) for c in case], ok=ok, finite=fin,
@@ -82,7 +90,7 @@ for case in CASES:
         all_ok = False
         log(step="equal", case=[str(c) for c in case], ok=False, error=repr(e)[:400])
         break
-log(step="equal_summary", ok=all_ok)
+log(step="equal_summary", ok=all_ok, ok_pingpong=all_ok_pp)
 
 
 def cuda_time(fn, warm=3, iters=20):
@@ -109,9 +117,9 @@ if all_ok or "--force-timing" in sys.argv:
             B, H, M, N, D, kind, causal, dt = case
             flops = 4.0 * B * H * M * N * D * (0.5 if causal else 1.0)
             res = {}
-            for persist in (False, True, False, True):
-                t = cuda_time(lambda: fwd(persist, q, k, v, bias, causal, 1.0, band, lo, hi))
-                res.setdefault("persist" if persist else "base", []).append(round(t * 1e3, 1))
+            for mode in ("base", "persist", "pingpong", "base", "persist", "pingpong"):
+                t = cuda_time(lambda: fwd(mode, q, k, v, bias, causal, 1.0, band, lo, hi))
+                res.setdefault(mode, []).append(round(t * 1e3, 1))
             log(step="timing", case=[str(c) for c in case], us=res,
                 tflops={n: round(flops / (min(v) * 1e-6) / 1e12, 1) for n, v in res.items()})
             del q, k, v, bias
