@@ -143,6 +143,7 @@ attn_fwd_pingpong_kernel(const __grid_constant__ AttnFwdKernelParams p, const in
             printf("b200t5: dynamic smem base not 1024-byte aligned\n");
             __trap();
         }
+        *reinterpret_cast<float*>(smem + L::kTmemSlot + 4) = 0.f;      // the zero word of the exp token (see the softmax loop)
         for (int i = 0; i < 2; ++i) {
             mbar_init(bars.q_full + i, 1);
             mbar_init(bars.q_empty + i, 1);
@@ -316,6 +317,8 @@ attn_fwd_pingpong_kernel(const __grid_constant__ AttnFwdKernelParams p, const in
         const uint8_t* const bias_smem = smem + L::kBias + qi * 2 * kBiasHalfBytes;
         const float* band = reinterpret_cast<const float*>(smem + L::kBias);   // [bias mode 3] shared by both warpgroups
         int band_h = -1;
+        const uint32_t token_zero = smem_u32(smem + L::kTmemSlot + 4);          // holds 0.0f (written before the first barrier)
+        const uint32_t token_dump = smem_u32(smem + L::kTmemSlot + 8 + 4 * qi); // write-only scratch word of this warpgroup
 
         // the exp token starts with warpgroup 0: warpgroup 1 pre-arrives on warpgroup 0's barrier
         if (qi == 1) named_bar_arrive(kTokenBar0 + 0, 256);
@@ -458,10 +461,14 @@ attn_fwd_pingpong_kernel(const __grid_constant__ AttnFwdKernelParams p, const in
                     m_ref = tmax;
                 }
                 const float m_safe = (m_ref == -INFINITY) ? 0.f : m_ref;
-                const float neg_m_log2 = -m_safe * kLog2e;
+                float neg_m_log2 = -m_safe * kLog2e;
 
                 // ---- exp phase: MUFU-bound; the two warpgroups take turns ----
                 named_bar_sync(kTokenBar0 + qi, 256);
+                // exp2 is pure register arithmetic, which ptxas schedules freely around a barrier (first build: 124 of the
+                // 128 MUFU.EX2 sat ABOVE the BAR.SYNC).  Memory operations are ordered against barriers, so the common
+                // operand of every exp2 takes a (zero) word read from shared memory after the barrier ...
+                neg_m_log2 += ld_shared_volatile_f32(token_zero);
                 uint32_t pk[kBN / 2];
                 float s0 = 0.f, s1 = 0.f;
 #pragma unroll
@@ -472,6 +479,8 @@ attn_fwd_pingpong_kernel(const __grid_constant__ AttnFwdKernelParams p, const in
                     s1 += e1;
                     pk[c / 2] = pack2<kBf16>(e0, e1);
                 }
+                // ... and the sum every exp2 feeds is written to shared memory before the token is handed over
+                st_shared_volatile_f32(token_dump, s0 + s1);
                 named_bar_arrive(kTokenBar0 + (qi ^ 1), 256);
                 l_sum = l_sum * alpha + (s0 + s1);
 

@@ -124,6 +124,16 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// volatile shared-memory accesses: unlike register arithmetic they keep their order against barriers, which makes them the
+// way to pin a stretch of pure arithmetic between two barrier instructions (attn_fwd_pingpong.cu)
+__device__ __forceinline__ float ld_shared_volatile_f32(uint32_t saddr) {
+    float v;
+    asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_shared_volatile_f32(uint32_t saddr, float v) {
+    asm volatile("st.volatile.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
+}
 
 // ------------------------------------------------------------------------------------------
 // mbarrier
