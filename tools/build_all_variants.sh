@@ -1,5 +1,7 @@
 #!/bin/bash
 # Developer tool: build the variant libraries of the prepared experiments, ~10 s each.
+# Each library is ~19 MB and travels with every gpurun snapshot: delete the ones a call does not need (and all of them
+# before the round ends -- the driver ships the tree as it is).
 set -e
 cd "$(dirname "$0")/.."
 python -m flasht5_b200.build > /dev/null
