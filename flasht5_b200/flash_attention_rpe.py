@@ -66,6 +66,7 @@ def constant_ends(lut_cpu: torch.Tensor, lut_zero: int) -> Tuple[int, int]:
     return i_lo - lut_zero, i_hi - lut_zero
 
 
+@torch.compiler.disable      # host-side table building (one device->host copy per new shape): not something to trace
 def bucket_lut(M: int, N: int, num_buckets: int, max_distance: int, bidirectional: bool, device):
     """(lut int32 on `device`, lut_zero, const_lo, const_hi) for relative positions -(M-1) .. N-1, cached.
     The buckets come from the reference formula evaluated on `device` (positional_encoding.py)."""
