@@ -46,7 +46,8 @@ __all__ = ["flash_attention_v2_rpe", "FlashAttentionRPE", "rpe_band", "attn_rpe_
 BAND_PAD = 255          # kernels.h: kRpeBandPad
 MAX_BAND_LEN = 8192     # kernels.h: kRpeMaxBandLen
 
-_LUT_CACHE = {}
+_LUT_CACHE = {}          # (M, N, num_buckets, max_distance, bidirectional, device) -> (lut, lut_zero, const_lo, const_hi)
+_LUT_CACHE_MAX = 64      # shapes a process meets are few; bound it anyway (oldest entry goes first)
 
 
 def constant_ends(lut_cpu: torch.Tensor, lut_zero: int) -> Tuple[int, int]:
@@ -78,6 +79,8 @@ def bucket_lut(M: int, N: int, num_buckets: int, max_distance: int, bidirectiona
             rel, bidirectional=bidirectional, num_buckets=num_buckets, max_distance=max_distance).to(torch.int32)
         lo, hi = constant_ends(lut.cpu(), M - 1)
         hit = (lut, M - 1, lo, hi)
+        if len(_LUT_CACHE) >= _LUT_CACHE_MAX:
+            _LUT_CACHE.pop(next(iter(_LUT_CACHE)))
         _LUT_CACHE[key] = hit
     return hit
 
