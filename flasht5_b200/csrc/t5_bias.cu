@@ -8,6 +8,7 @@
 // HBM-bound parts: the dense gather (writes H*M*N elements once, directly in the attention dtype -- no fp32
 // (1,H,M,N) intermediate) and the segmented sum.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -448,6 +449,15 @@ cudaError_t launch_t5_bias_bwd(const void* dbias, const int32_t* lut, int lut_ze
                                const int32_t* mem_pos, float* dtable, int H, int M, int N, int num_buckets, int dbias_dtype,
                                cudaStream_t stream) {
     if (num_buckets > kMaxBuckets) return cudaErrorInvalidValue;
+    {
+        // developer switch (B200T5_T5BIAS_BWD_TILES=1): the tile-parallel diagonal walk written for the in-kernel-bias backward
+        // (rpe_dtable_band_kernel, here over every tile of a dense 16-bit dBias) instead of the row-band kernel below, which
+        // measured 0.10-0.16 of the HBM roof (256 CTAs, one per SM, few bytes in flight).  Not yet run on hardware.
+        const char* v = getenv("B200T5_T5BIAS_BWD_TILES");
+        if (v && atoi(v) != 0 && ctx_pos == nullptr && mem_pos == nullptr && dbias_dtype != 2 && (M + 127) / 128 <= 65535 && H <= 65535)
+            return launch_rpe_dtable_band(dbias, N, 1, H, M, N, lut, lut_zero, lut_len, -(1 << 30), 1 << 30, dtable, num_buckets, false,
+                                          dbias_dtype == 1, stream);
+    }
     cudaError_t e = cudaMemsetAsync(dtable, 0, (size_t)num_buckets * H * sizeof(float), stream);
     if (e != cudaSuccess) return e;
     {

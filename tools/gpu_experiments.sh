@@ -5,7 +5,7 @@
 mkdir -p gpurun_out
 O=gpurun_out
 echo "== gated GPU tests (AdamWScale, relative-position backward level 2)" | tee $O/exp_summary.txt
-B200T5_ADAMW_GPU=1 B200T5_RPE_SKIP2_GPU=1 B200T5_RMSNORM_PREFETCH_GPU=1 timeout 200 python -m pytest tests/test_adamw_scaled.py tests/test_attention_rpe.py tests/test_norm_ce_gpu.py -m gpu -q > $O/exp_gated_tests.log 2>&1
+B200T5_ADAMW_GPU=1 B200T5_RPE_SKIP2_GPU=1 B200T5_RMSNORM_PREFETCH_GPU=1 B200T5_T5BIAS_TILES_GPU=1 timeout 200 python -m pytest tests/test_adamw_scaled.py tests/test_attention_rpe.py tests/test_norm_ce_gpu.py tests/test_positional_encoding.py -m gpu -q > $O/exp_gated_tests.log 2>&1
 tail -3 $O/exp_gated_tests.log | tee -a $O/exp_summary.txt
 echo "== relative-position backward: skip levels" | tee -a $O/exp_summary.txt
 timeout 120 python tools/rpe_skip_check.py > $O/exp_rpe_skip.log 2>&1
