@@ -110,6 +110,26 @@ __device__ __forceinline__ PPWork pp_decode(int w, const AttnFwdKernelParams& p,
 
 }  // namespace
 
+// Developer build (-DB200T5_FWD_TIMING): the CTA resident on SM `kPPTimedSm` stamps clock64 at the phase boundaries of
+// thread 0 of each softmax warpgroup for its first kPPTimedTiles score tiles; the launcher prints the two timelines.
+#ifdef B200T5_FWD_TIMING
+constexpr int kPPTimedSm = 17;
+constexpr int kPPTimedTiles = 28;
+__device__ long long g_pp_ts[2][kPPTimedTiles][8];   // [warpgroup][tile][stamp]
+__device__ int g_pp_ts_bid;
+__device__ __forceinline__ long long ppclk64() {
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+    return t;
+}
+#define PP_TS(t_, slot_)                                                                                   \
+    do {                                                                                                   \
+        if (ts_on && (t_) < (uint32_t)kPPTimedTiles) g_pp_ts[qi][t_][slot_] = ppclk64();                   \
+    } while (0)
+#else
+#define PP_TS(t_, slot_) do { } while (0)
+#endif
+
 template <int kD, bool kBf16, int kBiasMode, bool kCausal>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_pingpong_kernel(const __grid_constant__ AttnFwdKernelParams p, const int total_work, const int npairs) {
@@ -320,6 +340,15 @@ attn_fwd_pingpong_kernel(const __grid_constant__ AttnFwdKernelParams p, const in
         const uint32_t token_zero = smem_u32(smem + L::kTmemSlot + 4);          // holds 0.0f (written before the first barrier)
         const uint32_t token_dump = smem_u32(smem + L::kTmemSlot + 8 + 4 * qi); // write-only scratch word of this warpgroup
 
+#ifdef B200T5_FWD_TIMING
+        bool ts_on = false;
+        {
+            uint32_t smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            ts_on = smid == kPPTimedSm && r == 0;
+            if (ts_on && qi == 0) g_pp_ts_bid = blockIdx.x;
+        }
+#endif
         // the exp token starts with warpgroup 0: warpgroup 1 pre-arrives on warpgroup 0's barrier
         if (qi == 1) named_bar_arrive(kTokenBar0 + 0, 256);
 
@@ -352,6 +381,7 @@ attn_fwd_pingpong_kernel(const __grid_constant__ AttnFwdKernelParams p, const in
                 }
                 const int col0 = j * kBN;
                 float x[kBN];
+                PP_TS(T, 0);
 
                 // ---- dense bias tile -> registers before the scores are needed ----
                 uint32_t bw[kBN / 2];
@@ -381,6 +411,7 @@ attn_fwd_pingpong_kernel(const __grid_constant__ AttnFwdKernelParams p, const in
 
                 mbar_wait(bars.s_full + qi, T & 1);
                 tc_fence_after();
+                PP_TS(T, 1);
                 {
                     uint32_t(&xr)[kBN] = reinterpret_cast<uint32_t(&)[kBN]>(x);
                     tmem_ld32(tm_s + 0, reinterpret_cast<uint32_t(&)[32]>(xr[0]));
@@ -392,6 +423,7 @@ attn_fwd_pingpong_kernel(const __grid_constant__ AttnFwdKernelParams p, const in
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bars.s_empty + qi);
+                PP_TS(T, 2);
 
                 // ---- scores = S * sm_scale + bias and their row max, one straight-line block ----
                 auto row_max = [&]() -> float {
@@ -464,7 +496,9 @@ attn_fwd_pingpong_kernel(const __grid_constant__ AttnFwdKernelParams p, const in
                 float neg_m_log2 = -m_safe * kLog2e;
 
                 // ---- exp phase: MUFU-bound; the two warpgroups take turns ----
+                PP_TS(T, 3);
                 named_bar_sync(kTokenBar0 + qi, 256);
+                PP_TS(T, 4);
                 // exp2 is pure register arithmetic, which ptxas schedules freely around a barrier (first build: 124 of the
                 // 128 MUFU.EX2 sat ABOVE the BAR.SYNC).  Memory operations are ordered against barriers, so the common
                 // operand of every exp2 takes a (zero) word read from shared memory after the barrier ...
@@ -482,6 +516,7 @@ attn_fwd_pingpong_kernel(const __grid_constant__ AttnFwdKernelParams p, const in
                 // ... and the sum every exp2 feeds is written to shared memory before the token is handed over
                 st_shared_volatile_f32(token_dump, s0 + s1);
                 named_bar_arrive(kTokenBar0 + (qi ^ 1), 256);
+                PP_TS(T, 5);
                 l_sum = l_sum * alpha + (s0 + s1);
 
                 if (j > 0) {
@@ -508,12 +543,14 @@ attn_fwd_pingpong_kernel(const __grid_constant__ AttnFwdKernelParams p, const in
                         }
                     }
                 }
+                PP_TS(T, 6);
                 tmem_st32(tm_p + 0, reinterpret_cast<const uint32_t(&)[32]>(pk[0]));
                 tmem_st32(tm_p + 32, reinterpret_cast<const uint32_t(&)[32]>(pk[32]));
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bars.p_full + qi);
+                PP_TS(T, 7);
                 ++T;
             }
 
@@ -583,6 +620,26 @@ static cudaError_t launch_pp_inst(const AttnFwdKernelParams& kp, cudaStream_t st
     const int grid = static_cast<int>(total < num_sms ? total : num_sms);
     kern<<<grid, kThreads, L::kTotal, stream>>>(kp, static_cast<int>(total), npairs);
     count_launch();
+#ifdef B200T5_FWD_TIMING
+    {
+        cudaDeviceSynchronize();
+        static long long ts[2][kPPTimedTiles][8];
+        int bid = -1;
+        cudaMemcpyFromSymbol(ts, g_pp_ts, sizeof(ts));
+        cudaMemcpyFromSymbol(&bid, g_pp_ts_bid, sizeof(int));
+        const long long t0 = ts[0][0][0] < ts[1][0][0] ? ts[0][0][0] : ts[1][0][0];
+        printf("PP_TIMING sm %d (block %d, grid %d); thread 0 of each softmax warpgroup per score tile: [tile start, S ready, S in regs, "
+               "bias+max done, token acquired, exp done (token passed), P V(t-1) done, P stored]\n", kPPTimedSm, bid, grid);
+        for (int j = 0; j < kPPTimedTiles; ++j) {
+            for (int q = 0; q < 2; ++q) {
+                printf("  t=%d wg%d:", j, q);
+                for (int k = 0; k < 8; ++k) printf(" %7lld", ts[q][j][k] - t0);
+                printf(q ? "\n" : "   |");
+            }
+        }
+        fflush(stdout);
+    }
+#endif
     return cudaGetLastError();
 }
 

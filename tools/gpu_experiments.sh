@@ -25,6 +25,8 @@ for lib in flasht5_b200/libb200t5_hl_*.so; do
   B200T5_FWD_PERSIST=1 B200T5_LIB=$PWD/$lib timeout 100 python tools/lib_ab_check.py --compare /tmp/ab_base.pt --tol > $O/exp_ab_${n}_persist.log 2>&1
   grep -E '"lib"' $O/exp_ab_${n}_persist.log | sed 's/^/persist: /' | cut -c1-300 | tee -a $O/exp_summary.txt
 done
+echo "== ping-pong forward timeline" | tee -a $O/exp_summary.txt
+[ -f flasht5_b200/libb200t5_hl_timing.so ] && B200T5_FWD_PINGPONG=1 B200T5_LIB=$PWD/flasht5_b200/libb200t5_hl_timing.so timeout 60 python tools/fwd_timeline.py bias > $O/exp_timeline_pingpong.txt 2>&1
 echo "== persistent forward timeline, with and without the stagger" | tee -a $O/exp_summary.txt
 for n in hl_timing hl_timing_stagger; do
   [ -f flasht5_b200/libb200t5_$n.so ] || continue
