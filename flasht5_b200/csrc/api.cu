@@ -310,13 +310,16 @@ static int attn_fwd_impl(const b200t5_attn_params* p, const b200t5_rpe_params* r
     cudaError_t e;
     {
         ProfScope prof(B200T5_KERNEL_ATTN_FWD, static_cast<cudaStream_t>(p->stream));
-        // the persistent schedule covers the TMA / in-kernel bias modes; the pointer path (mode 2) keeps one CTA per block
-        const bool persist = fwd_persistent_enabled() && mode != 2;
+        // schedules of the same forward: one CTA per query block (default), persistent, two query tiles per CTA.  The two
+        // developer schedules cover the TMA / in-kernel bias modes; the pointer path (mode 2) always takes the default.
+        const bool bf16 = p->dtype == B200T5_BF16, causal = p->causal != 0;
+        cudaStream_t stream = static_cast<cudaStream_t>(p->stream);
         if (fwd_pingpong_enabled() && mode != 2 && p->D <= 64)
-            e = launch_attn_fwd_pingpong(kp, p->D, p->dtype == B200T5_BF16, mode, p->causal != 0, static_cast<cudaStream_t>(p->stream));
+            e = launch_attn_fwd_pingpong(kp, p->D, bf16, mode, causal, stream);
+        else if (fwd_persistent_enabled() && mode != 2)
+            e = launch_attn_fwd_persist(kp, p->D, bf16, mode, causal, stream);
         else
-        e = persist ? launch_attn_fwd_persist(kp, p->D, p->dtype == B200T5_BF16, mode, p->causal != 0, static_cast<cudaStream_t>(p->stream))
-                    : launch_attn_fwd(kp, p->D, p->dtype == B200T5_BF16, mode, p->causal != 0, static_cast<cudaStream_t>(p->stream));
+            e = launch_attn_fwd(kp, p->D, bf16, mode, causal, stream);
     }
     if (e != cudaSuccess) return fail_cuda(e, "attn_fwd launch");
     return 0;
