@@ -45,6 +45,16 @@ constexpr float kLog2e = 1.4426950408889634f;
 #ifndef B200T5_BIAS_FHADD
 #define B200T5_BIAS_FHADD 0     // developer switch, see attn_fwd.cu
 #endif
+// Developer switch: the two compute warpgroups of a CTA work on the two column halves of the same tile in lock-step, so the
+// two warps that share a scheduler run their MUFU-bound P / dS chunks at the same time (each at half rate) and load S / dP /
+// bias at the same time (MUFU idle) -- the pattern the forward timeline exposed (attn_fwd_pingpong.cu).  With
+// B200T5_BWD_PINGPONG=1 the warpgroups pass a token through two named barriers around every 32-column chunk of math, so one
+// computes while the other waits for its tcgen05.ld and reads its bias.  Not yet run on hardware.
+#ifndef B200T5_BWD_PINGPONG
+#define B200T5_BWD_PINGPONG 0
+#endif
+static_assert(!(B200T5_BWD_PINGPONG && B200T5_BIAS_FHADD), "the two developer switches are not combined yet");
+constexpr int kBwdToken0 = 4;       // named barriers 4, 5 (1-3 are taken)
 
 template <int kD>
 struct Bwd2Cfg {
@@ -213,6 +223,9 @@ attn_bwd_kernel_v2(const __grid_constant__ AttnBwdKernelParams p) {
 
     if (threadIdx.x == 0) {
         if ((smem_u32(smem) & 1023u) != 0) __trap();
+#if B200T5_BWD_PINGPONG
+        *reinterpret_cast<float*>(smem + C::kTmemSlot + 4) = 0.f;
+#endif
         mbar_init(kv_full, 1);
         for (int i = 0; i < C::kQStages; ++i) {
             mbar_init(qdo_full + i, 1);
@@ -434,6 +447,11 @@ attn_bwd_kernel_v2(const __grid_constant__ AttnBwdKernelParams p) {
         // surface; their dS is summed here (fp32) and leaves the CTA as two numbers (one per side)
         const bool rpe_skip = kBiasMode == 3 && p.rpe.dconst != nullptr;
         float ds_const_lo = 0.f, ds_const_hi = 0.f;
+#if B200T5_BWD_PINGPONG
+        const uint32_t token_zero = smem_u32(smem + C::kTmemSlot + 4);            // holds 0.0f
+        const uint32_t token_dump = smem_u32(smem + C::kTmemSlot + 8 + 4 * wg);   // write-only scratch word
+        if (wg == 1) named_bar_arrive(kBwdToken0 + 0, 256);                       // the token starts with warpgroup 0
+#endif
 
         // row statistics are prefetched one block ahead (global latency off the critical path)
         float L_next = 0.f, dlt_next = 0.f;
@@ -540,16 +558,29 @@ attn_bwd_kernel_v2(const __grid_constant__ AttnBwdKernelParams p) {
 #pragma unroll
                     for (int e = 0; e < 32; ++e) bv[e] = 0.f;
                 }
+#if B200T5_BWD_PINGPONG
+                // my turn for the MUFU-bound chunk.  ptxas moves register arithmetic across barriers (attn_fwd_pingpong.cu): the
+                // operand every exp2 of the chunk shares takes a zero read from shared memory after the barrier ...
+                named_bar_sync(kBwdToken0 + wg, 256);
+                const float nl = neg_L_log2 + ld_shared_volatile_f32(token_zero);
+#else
+                const float nl = neg_L_log2;
+#endif
                 if (kBiasMode == 3 && rpe_skip && rpe_const) {
                     float* acc = (col0 - mrow0 + (kBN - 1) <= p.rpe.const_lo) ? &ds_const_lo : &ds_const_hi;
                     if (need_mask)
-                        p_ds_chunk<kBf16, true, true>(sr, dr, bv, scale_log2, neg_L_log2, dlt, lim - ch * 32, pp[ch], dd[ch], acc);
+                        p_ds_chunk<kBf16, true, true>(sr, dr, bv, scale_log2, nl, dlt, lim - ch * 32, pp[ch], dd[ch], acc);
                     else
-                        p_ds_chunk<kBf16, false, true>(sr, dr, bv, scale_log2, neg_L_log2, dlt, 0, pp[ch], dd[ch], acc);
+                        p_ds_chunk<kBf16, false, true>(sr, dr, bv, scale_log2, nl, dlt, 0, pp[ch], dd[ch], acc);
                 } else if (need_mask)
-                    p_ds_chunk<kBf16, true>(sr, dr, bv, scale_log2, neg_L_log2, dlt, lim - ch * 32, pp[ch], dd[ch]);
+                    p_ds_chunk<kBf16, true>(sr, dr, bv, scale_log2, nl, dlt, lim - ch * 32, pp[ch], dd[ch]);
                 else
-                    p_ds_chunk<kBf16, false>(sr, dr, bv, scale_log2, neg_L_log2, dlt, 0, pp[ch], dd[ch]);
+                    p_ds_chunk<kBf16, false>(sr, dr, bv, scale_log2, nl, dlt, 0, pp[ch], dd[ch]);
+#if B200T5_BWD_PINGPONG
+                // ... and a word that depends on the first and the last results of the chunk is stored before the token moves on
+                st_shared_volatile_f32(token_dump, __uint_as_float(pp[ch][0] ^ pp[ch][15] ^ dd[ch][0] ^ dd[ch][15]));
+                named_bar_arrive(kBwdToken0 + (wg ^ 1), 256);
+#endif
             }
             if (kBiasMode == 1) {
                 fence_proxy_async_smem();                    // bias reads complete before TMA refills the half
@@ -612,6 +643,9 @@ attn_bwd_kernel_v2(const __grid_constant__ AttnBwdKernelParams p) {
             }
         }
 
+#if B200T5_BWD_PINGPONG
+        if (wg == 0) named_bar_sync(kBwdToken0 + 0, 256);        // consume the arrival warpgroup 1 posted after its last chunk
+#endif
         // ---- tail: dQ of the last block, then dV (warpgroup 0) and dK * sm_scale (warpgroup 1) ----
         if (n_iter > 0) {
             mbar_wait(dq_full, (n_iter - 1) & 1);            // every MMA of this CTA has completed

@@ -11,4 +11,6 @@ tools/build_variant.sh --headline hl_fhadd_poly2 "-DB200T5_BIAS_FHADD=1 -DB200T5
 tools/build_variant.sh --headline hl_timing "-DB200T5_FWD_TIMING"
 tools/build_variant.sh --headline hl_timing_stagger "-DB200T5_FWD_TIMING -DB200T5_PERSIST_STAGGER_NS=700"
 tools/build_variant.sh --headline hl_stagger "-DB200T5_PERSIST_STAGGER_NS=700"
+tools/build_variant.sh --headline hl_bwdpp "-DB200T5_BWD_PINGPONG=1"
+tools/build_variant.sh --headline hl_bwdpp_poly2 "-DB200T5_BWD_PINGPONG=1 -DB200T5_EXP2_POLY=2"
 ls -la flasht5_b200/libb200t5_*.so

@@ -4,7 +4,8 @@
 #   usage: tools/build_variant.sh [--headline] <name> "<extra nvcc flags>"
 # --headline: only the D = 64 / bf16 instantiations (-DB200T5_HEADLINE_ONLY) and the stock D = 128 backward object:
 #             ~20 s to build and a ~5 MB library instead of ~75 s / 25 MB.
-# Known switches: -DB200T5_EXP2_POLY=K  -DB200T5_PRODUCER_SLEEP_NS=N  -DB200T5_FWD_TIMING  -DB200T5_BWD_TIMING
+# Known switches: -DB200T5_EXP2_POLY=K  -DB200T5_BIAS_FHADD=1  -DB200T5_BWD_PINGPONG=1  -DB200T5_PERSIST_STAGGER_NS=N
+#                 -DB200T5_PRODUCER_SLEEP_NS=N  -DB200T5_FWD_TIMING  -DB200T5_BWD_TIMING
 set -e
 HEADLINE=0
 if [ "$1" == "--headline" ]; then HEADLINE=1; shift; fi
