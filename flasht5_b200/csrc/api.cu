@@ -219,9 +219,10 @@ static bool fwd_persistent_enabled() {
     return v ? atoi(v) != 0 : kFwdPersistentDefault;
 }
 // B200T5_FWD_PINGPONG=1: the two-query-tile forward (attn_fwd_pingpong.cu; developer kernel, not yet run on hardware)
+constexpr bool kFwdPingpongDefault = false;       // flip after it has been validated and timed on hardware
 static bool fwd_pingpong_enabled() {
     const char* v = getenv("B200T5_FWD_PINGPONG");
-    return v && atoi(v) != 0;
+    return v ? atoi(v) != 0 : kFwdPingpongDefault;
 }
 
 // Backward of the relative-position operator: B200T5_RPE_SKIP_CONST=1 lets tiles that lie entirely beyond a constant end
