@@ -30,7 +30,7 @@ from flasht5_b200 import flash_attention_rpe as rpe                   # noqa: E4
 DEV = "cuda:0"
 _t = lambda a: torch.from_numpy(np.asarray(a))   # noqa: E731
 ok_all = True
-for skip in ("0", "1"):
+for skip in ("0", "1", "2"):
     os.environ["B200T5_RPE_SKIP_CONST"] = skip
     try:
         for path in sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "rpe_*.npz"))):
@@ -46,7 +46,9 @@ for skip in ("0", "1"):
             ok_all &= ok
             log(step="golden", skip=skip, case=os.path.basename(path), relF=errs, ok=ok)
         for (B, H, M, N, D, causal) in [(2, 4, 512, 512, 64, False), (1, 2, 1024, 1024, 64, True), (3, 8, 1024, 1024, 64, False),
-                                        (1, 3, 700, 1300, 32, False), (2, 2, 640, 384, 16, True)]:
+                                        (1, 3, 700, 1300, 32, False)]:
+            # (the causal M > N shape of tests/test_attention_rpe.py::test_cuda_constant_tile_skip is left to that test: every
+            #  visible position falls into one bucket there, the exact table gradient is 0 and a relative error means nothing)
             g = torch.Generator().manual_seed(11)
             mk = lambda s: torch.randn(B, s, H, D, generator=g).to(torch.bfloat16).to(DEV).permute(0, 2, 1, 3)   # noqa: E731
             q, k, v, do = mk(M), mk(N), mk(N), mk(M)
@@ -78,7 +80,7 @@ if ok_all:
     lut, zero, lo, hi = rpe.bucket_lut(S, S, 32, 128, True, q.device)
     band = torch.ops.b200t5.rpe_band(table, lut, zero, lo, hi, torch.bfloat16)
     o, L = torch.ops.b200t5.attn_rpe_fwd(q, k, v, band, lo, hi, False, 1.0)
-    for skip in ("0", "1", "0", "1"):
+    for skip in ("0", "1", "2", "0", "1", "2"):
         os.environ["B200T5_RPE_SKIP_CONST"] = skip
         for _ in range(3):
             torch.ops.b200t5.attn_rpe_bwd(o, do, q, k, v, band, lut, zero, lo, hi, 32, L, False, 1.0)
