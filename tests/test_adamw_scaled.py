@@ -160,6 +160,70 @@ def test_constructor_mirrors_reference_and_there_is_no_cpu_fallback():
         opt.step()
 
 
+def _kernel_restated(p, g, m, v, c, step, lr, b1, b2, eps, wd, cb, p_dt, s_dt):
+    """csrc/adamw.cu restated with torch fp32 ops (adamw_rms_kernel + adamw_elem, same order, same rounding points;
+    multiply-adds left unfused, which moves results by at most an fp32 ulp).  All tensors fp32 holding dtype-representable
+    values; returns the same."""
+    rnd_p = lambda x: x.to(p_dt).float()   # noqa: E731
+    rnd_s = lambda x: x.to(s_dt).float()   # noqa: E731
+    f32 = lambda x: float(torch.tensor(x, dtype=torch.float32))   # noqa: E731
+    ss_base, ss_floor = step_size_terms(step, lr, b1, b2, cb)
+    # pass 1 + 2: sum of squares -> norm -> rms, each a tensor of the parameter dtype
+    norm = rnd_p(torch.sqrt((p * p).sum(dtype=torch.float32)))
+    rms = rnd_p(norm / f32(p.numel() ** 0.5))
+    if float(rms) > f32(1e-3):
+        ss = torch.tensor(f32(ss_base)) * rms
+        if (not cb) and p_dt != torch.float32:
+            ss = rnd_p(ss)
+        ss = float(ss)
+    else:
+        ss = f32(ss_floor)
+    value = -ss
+    # pass 3
+    beta1, beta2, om1, om2, epsf = f32(b1), f32(b2), f32(1.0 - b1), f32(1.0 - b2), f32(eps)
+    m = rnd_s(m * beta1)
+    m = rnd_s(m + om1 * g)
+    v = rnd_s(v * beta2)
+    v = rnd_s(v + om2 * (g * g))
+    d = rnd_s(torch.sqrt(v))
+    d = rnd_s(d + epsf)
+    q = value * (m / d)
+    if c is not None:
+        c = rnd_p(c + q)
+        old = p
+        p = rnd_p(p + c)
+        lost = rnd_p(old - p)
+        c = rnd_p(c + lost)
+    else:
+        p = rnd_p(p + q)
+    if wd > 0.0:
+        p = rnd_p(p + f32(-lr * wd) * p)
+    return p, m, v, c
+
+
+@pytest.mark.parametrize("path", FILES, ids=IDS)
+def test_kernel_arithmetic_restated_matches_reference_golden(path):
+    """The CUDA kernels' arithmetic, restated line by line on the CPU, against the reference golden vectors at the bars
+    of the GPU test below: catches a wrong order of operations or a missing rounding before the kernels ever run."""
+    z, c = _case(path)
+    tol = 1.6e-2 if c["dt"] == torch.bfloat16 else 2e-6
+    for j in range(c["n"]):
+        p = _t(z[f"p0_{j}"], c["dt"]).float()
+        m, v = torch.zeros_like(p), torch.zeros_like(p)
+        comp = torch.zeros_like(p) if (c["kahan"] and c["dt"] != torch.float32) else None
+        for step in range(3):
+            g = _t(z[f"g{step}_{j}"], c["dt"]).float()
+            p, m, v, comp = _kernel_restated(p, g, m, v, comp, step + 1, c["lr"], c["b1"], c["b2"], c["eps"], c["wd"], c["cb"],
+                                             c["dt"], c["dt"])
+        for nm, mine in (("p", p), ("m", m), ("v", v)):
+            ref = _t(z[f"{nm}{j}"])
+            err = (mine - ref).abs().max()
+            assert err <= tol * ref.abs().max() + 1e-12, (j, nm, float(err))
+        if comp is not None:
+            eff_ref = _t(z[f"p{j}"]) + _t(z[f"comp{j}"])
+            assert ((p + comp) - eff_ref).abs().max() <= 2e-3 * eff_ref.abs().max()
+
+
 # ------------------------------------------------------------------------------------------------------------
 # GPU
 # ------------------------------------------------------------------------------------------------------------
