@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libb200t5.so")
-SOURCES = ["attn_fwd.cu", "attn_fwd_persist.cu", "attn_fwd_pingpong.cu", "attn_bwd.cu", "attn_bwd_v2.cu", "norm_ce.cu", "t5_bias.cu", "adamw.cu", "api.cu"]
+SOURCES = ["attn_fwd.cu", "attn_bwd.cu", "attn_bwd_v3.cu", "norm_ce.cu", "t5_bias.cu", "adamw.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

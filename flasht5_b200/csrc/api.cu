@@ -206,35 +206,19 @@ static int bias_mode_of(const b200t5_attn_params* p) {
 }
 
 static int round_up8(int x) { return (x + 7) / 8 * 8; }
-constexpr bool kFwdPersistentDefault = false;
 static int check_dtype3(int dt, const char* what) {
     if (dt == B200T5_F16 || dt == B200T5_BF16 || dt == B200T5_F32) return 0;
     return fail(B200T5_ERR_UNSUPPORTED, "%s dtype %d not in {fp16, bf16, fp32}", what, dt);
 }
 
-// Forward schedule: B200T5_FWD_PERSIST=0/1 selects one-CTA-per-block (attn_fwd.cu) or persistent (attn_fwd_persist.cu);
-// read on every call so that a developer A/B script can flip it inside one process.
-static bool fwd_persistent_enabled() {
-    const char* v = getenv("B200T5_FWD_PERSIST");
-    return v ? atoi(v) != 0 : kFwdPersistentDefault;
-}
-// B200T5_FWD_PINGPONG=1: the two-query-tile forward (attn_fwd_pingpong.cu; developer kernel, not yet run on hardware)
-constexpr bool kFwdPingpongDefault = false;       // flip after it has been validated and timed on hardware
-static bool fwd_pingpong_enabled() {
-    const char* v = getenv("B200T5_FWD_PINGPONG");
-    return v ? atoi(v) != 0 : kFwdPingpongDefault;
-}
-
-// Backward of the relative-position operator: B200T5_RPE_SKIP_CONST=1 lets tiles that lie entirely beyond a constant end
-// of the bucket table skip their dS store (their dS is summed in the kernel).  Built after this round's GPU budget was
-// spent: compiled and reviewed, not yet run on hardware, hence off by default.  Read on every call (A/B inside one process).
-constexpr int kRpeSkipConstDefault = 0;
-// 0: every tile stores dS.  1: constant tiles keep dS in the kernel (validated on B200, untimed).  2: as 1, and the table
-// gradient is reduced straight from the non-constant tiles of the dS surface (rpe_dtable_band_kernel; not yet run).
-static int rpe_skip_const_level() {
-    const char* v = getenv("B200T5_RPE_SKIP_CONST");
-    return v ? atoi(v) : kRpeSkipConstDefault;
-}
+// Backward of the relative-position operator (compile-time; the A/B builds of round 2 chose level 2):
+//   0: every tile stores dS, dense (1, H, M, N) scratch, producer backward folds it into the table gradient
+//   1: half tiles entirely beyond a constant end of the bucket table keep their dS in the kernel (two fp32 sums per CTA)
+//   2: as 1, and the table gradient is folded straight from the non-constant tiles of the dS surface (no dense scratch)
+#ifndef B200T5_RPE_SKIP_LEVEL
+#define B200T5_RPE_SKIP_LEVEL 2
+#endif
+static int rpe_skip_const_level() { return B200T5_RPE_SKIP_LEVEL; }
 static bool rpe_skip_const_enabled() { return rpe_skip_const_level() != 0; }
 
 // ---- in-kernel relative-position bias (bias mode 3) ----
@@ -311,16 +295,9 @@ static int attn_fwd_impl(const b200t5_attn_params* p, const b200t5_rpe_params* r
     cudaError_t e;
     {
         ProfScope prof(B200T5_KERNEL_ATTN_FWD, static_cast<cudaStream_t>(p->stream));
-        // schedules of the same forward: one CTA per query block (default), persistent, two query tiles per CTA.  The two
-        // developer schedules cover the TMA / in-kernel bias modes; the pointer path (mode 2) always takes the default.
         const bool bf16 = p->dtype == B200T5_BF16, causal = p->causal != 0;
         cudaStream_t stream = static_cast<cudaStream_t>(p->stream);
-        if (fwd_pingpong_enabled() && mode != 2 && p->D <= 64)
-            e = launch_attn_fwd_pingpong(kp, p->D, bf16, mode, causal, stream);
-        else if (fwd_persistent_enabled() && mode != 2)
-            e = launch_attn_fwd_persist(kp, p->D, bf16, mode, causal, stream);
-        else
-            e = launch_attn_fwd(kp, p->D, bf16, mode, causal, stream);
+        e = launch_attn_fwd(kp, p->D, bf16, mode, causal, stream);
     }
     if (e != cudaSuccess) return fail_cuda(e, "attn_fwd launch");
     return 0;
@@ -334,8 +311,9 @@ extern "C" int b200t5_attn_rpe_fwd(const b200t5_attn_params* p, const b200t5_rpe
 
 namespace {
 struct BwdWorkspace {
-    size_t delta_off, dq_off, ds_off, ds_bytes, dbias_off, dconst_off, total;
-    int n_pad, ds_groups, ds_use_reduce, dq_groups;
+    size_t delta_off, dq_off, ds_off, ds_bytes, bias_t_off, dbias_off, dconst_off, total;
+    int ds_pitch, ds_groups, ds_use_reduce, dq_groups;
+    bool transposed;        // D <= 64: the v3 kernel (dS surface and bias copy are (.., N, M)); D = 128: (.., M, N)
 };
 // has_rpe: the bias is the in-kernel relative-position bias, i.e. a (1, H, M, N) bias whose dense gradient is only
 // an intermediate (kept in the workspace and folded into the (num_buckets, H) table gradient).
@@ -343,7 +321,8 @@ BwdWorkspace bwd_workspace_layout(const b200t5_attn_params* p, bool has_rpe = fa
     BwdWorkspace w;
     auto align = [](size_t x) { return (x + 255) / 256 * 256; };
     const size_t rows = (size_t)p->B * p->H * p->M;
-    w.n_pad = round_up8(p->N);
+    w.transposed = p->D <= 64;
+    w.ds_pitch = w.transposed ? round_up8(p->M) : round_up8(p->N);
     w.delta_off = 0;
     w.dq_off = align(rows * sizeof(float));
     // dQ group surface: <= 4 key blocks accumulate (16-bit, at L2) into one group; <= 8 groups
@@ -370,11 +349,14 @@ BwdWorkspace bwd_workspace_layout(const b200t5_attn_params* p, bool has_rpe = fa
         } else {
             w.ds_groups = p->B;
         }
-        ds_bytes = (size_t)w.ds_groups * p->H * p->M * (size_t)w.n_pad * 2;
+        ds_bytes = (size_t)w.ds_groups * p->H * (size_t)(w.transposed ? p->N : p->M) * (size_t)w.ds_pitch * 2;
     }
     w.ds_bytes = ds_bytes;
-    w.dbias_off = w.ds_off + align(ds_bytes);
-    w.dconst_off = w.dbias_off + (has_rpe ? align((size_t)p->H * p->M * (size_t)p->N * 2) : 0);
+    w.bias_t_off = w.ds_off + align(ds_bytes);
+    const size_t bias_t_bytes = (w.transposed && p->bias) ? (size_t)p->bias_B * p->bias_H * (size_t)p->N * (size_t)w.ds_pitch * 2 : 0;
+    w.dbias_off = w.bias_t_off + align(bias_t_bytes);
+    const bool dense_scratch = has_rpe && !(w.transposed && rpe_skip && rpe_skip_const_level() >= 2);
+    w.dconst_off = w.dbias_off + (dense_scratch ? align((size_t)p->H * p->M * (size_t)p->N * 2) : 0);
     w.total = w.dconst_off + (has_rpe ? align((size_t)p->H * 2 * sizeof(float)) : 0);
     return w;
 }
@@ -414,10 +396,12 @@ static int attn_bwd_impl(const b200t5_attn_params* p, const b200t5_rpe_params* r
 
     cudaStream_t stream = static_cast<cudaStream_t>(p->stream);
     const bool bf16 = p->dtype == B200T5_BF16;
+    const bool causal = p->causal != 0;
     uint8_t* ws = static_cast<uint8_t*>(p->workspace);
     float* delta = reinterpret_cast<float*>(ws + w.delta_off);
     void* dq_ws = ws + w.dq_off;
     void* ds_ws = ws + w.ds_off;
+    const int G = w.ds_groups > 0 ? w.ds_groups : 1;
 
     // delta, zero-fill of the dQ group surface and (when dS is reduce-added) of the dS group surface: one launch
     cudaError_t e = launch_attn_bwd_preprocess(p->o, p->o_strides, p->dout, p->do_strides, delta, dq_ws, w.dq_groups, p->B, p->H, p->M, p->D, bf16,
@@ -434,7 +418,8 @@ static int attn_bwd_impl(const b200t5_attn_params* p, const b200t5_rpe_params* r
     if ((rc = make_map_4d(&kp.map_do, p->dout, 2, dt, p->D, p->M, p->H, p->B, p->do_strides[2], p->do_strides[1], p->do_strides[0], boxd, 128, "dout"))) return rc;
     if ((rc = make_map_4d(&kp.map_dq, dq_ws, 2, dt, p->D, p->M, p->H, (uint64_t)w.dq_groups * p->B, p->D, (int64_t)p->M * p->D, (int64_t)p->H * p->M * p->D, boxd, 128, "dq group surface", true))) return rc;
     kp.dq_groups = w.dq_groups;
-    const int mode = rpe ? 3 : bias_mode_of(p);
+    // D <= 64: every dense bias goes through the transposed copy (which also absorbs unaligned rows); D = 128: TMA or pointers
+    const int mode = rpe ? 3 : (p->bias ? (w.transposed ? 1 : bias_mode_of(p)) : 0);
     float* dconst = nullptr;
     if (mode == 3) {
         fill_rpe_band(&kp.rpe, rpe);
@@ -445,20 +430,34 @@ static int attn_bwd_impl(const b200t5_attn_params* p, const b200t5_rpe_params* r
             kp.rpe.dconst = dconst;
         }
     }
-    if (mode == 1) {
-        if ((rc = make_map_4d(&kp.map_bias, p->bias, 2, dt, p->N, p->M, p->bias_H, p->bias_B, p->bias_strides[2], p->bias_strides[1], p->bias_strides[0], 64, 128, "bias"))) return rc;
-    } else if (mode == 2) {
-        kp.bias = p->bias;
-        kp.bias_sb = p->bias_strides[0];
-        kp.bias_sh = p->bias_strides[1];
-        kp.bias_sm = p->bias_strides[2];
-        kp.bias_sn = p->bias_strides[3];
+    if (w.transposed) {
+        if (mode == 1) {
+            void* bias_t = ws + w.bias_t_off;
+            e = launch_bias_transpose(p->bias, p->bias_strides, bias_t, p->bias_B, p->bias_H, p->M, p->N, w.ds_pitch, stream);
+            if (e != cudaSuccess) return fail_cuda(e, "bias_transpose launch");
+            if ((rc = make_map_4d(&kp.map_bias, bias_t, 2, dt, p->M, p->N, p->bias_H, p->bias_B, w.ds_pitch, (int64_t)p->N * w.ds_pitch, (int64_t)p->bias_H * p->N * w.ds_pitch, 64, 128, "transposed bias"))) return rc;
+        }
+        if (mode != 0) {
+            if ((rc = make_map_4d(&kp.map_ds, ds_ws, 2, dt, p->M, p->N, p->H, G, w.ds_pitch, (int64_t)p->N * w.ds_pitch, (int64_t)p->H * p->N * w.ds_pitch, 64, 128, "dS workspace (transposed)"))) return rc;
+        }
+        kp.k = p->k; kp.k_sb = p->k_strides[0]; kp.k_sh = p->k_strides[1]; kp.k_sn = p->k_strides[2];
+        kp.v = p->v; kp.v_sb = p->v_strides[0]; kp.v_sh = p->v_strides[1]; kp.v_sn = p->v_strides[2];
+    } else {
+        if (mode == 1) {
+            if ((rc = make_map_4d(&kp.map_bias, p->bias, 2, dt, p->N, p->M, p->bias_H, p->bias_B, p->bias_strides[2], p->bias_strides[1], p->bias_strides[0], 64, 128, "bias"))) return rc;
+        } else if (mode == 2) {
+            kp.bias = p->bias;
+            kp.bias_sb = p->bias_strides[0];
+            kp.bias_sh = p->bias_strides[1];
+            kp.bias_sm = p->bias_strides[2];
+            kp.bias_sn = p->bias_strides[3];
+        }
+        if (mode != 0) {
+            // dS tiles always go to the (B, H, M, n_pad) 16-bit workspace through TMA stores
+            if ((rc = make_map_4d(&kp.map_ds, ds_ws, 2, dt, p->N, p->M, p->H, G, w.ds_pitch, (int64_t)p->M * w.ds_pitch, (int64_t)p->H * p->M * w.ds_pitch, 64, 128, "dS workspace"))) return rc;
+        }
     }
-    if (mode != 0) {
-        // dS tiles always go to the (B, H, M, n_pad) 16-bit workspace through TMA stores
-        if ((rc = make_map_4d(&kp.map_ds, ds_ws, 2, dt, p->N, p->M, p->H, w.ds_groups, w.n_pad, (int64_t)p->M * w.n_pad, (int64_t)p->H * p->M * w.n_pad, 64, 128, "dS workspace"))) return rc;
-    }
-    kp.ds_groups = w.ds_groups > 0 ? w.ds_groups : 1;
+    kp.ds_groups = G;
     kp.ds_use_reduce = w.ds_use_reduce;
     kp.dk = p->dk; kp.dk_sb = p->dk_strides[0]; kp.dk_sh = p->dk_strides[1]; kp.dk_sn = p->dk_strides[2];
     kp.dv = p->dv; kp.dv_sb = p->dv_strides[0]; kp.dv_sh = p->dv_strides[1]; kp.dv_sn = p->dv_strides[2];
@@ -472,43 +471,48 @@ static int attn_bwd_impl(const b200t5_attn_params* p, const b200t5_rpe_params* r
     kp.sm_scale = p->sm_scale;
     {
         ProfScope prof(B200T5_KERNEL_ATTN_BWD, stream);
-        e = launch_attn_bwd(kp, p->D, bf16, mode, p->causal != 0, stream);
+        e = w.transposed ? launch_attn_bwd_v3(kp, p->D, bf16, mode, causal, stream) : launch_attn_bwd(kp, p->D, bf16, mode, causal, stream);
     }
     if (e != cudaSuccess) return fail_cuda(e, "attn_bwd launch");
 
-    if (rpe && dconst && rpe_skip_const_level() >= 2) {
-        // developer path: dQ conversion alone, then the table gradient straight from the non-constant tiles of the surface
+    if (rpe && dconst && w.transposed && rpe_skip_const_level() >= 2) {
+        // dQ conversion alone, then the table gradient straight from the non-constant tiles of the surface
         e = launch_attn_bwd_dq_convert(dq_ws, w.dq_groups, p->dq, p->dq_strides, p->B, p->H, p->M, p->D, p->sm_scale, bf16, stream);
         if (e != cudaSuccess) return fail_cuda(e, "attn_bwd_dq_convert launch");
-        e = launch_rpe_dtable_band(ds_ws, w.n_pad, w.ds_groups > 0 ? w.ds_groups : 1, p->H, p->M, p->N, rpe->lut, rpe->lut_zero, rpe->lut_len,
-                                   rpe->const_lo, rpe->const_hi, rpe->dtable, rpe->num_buckets, p->causal != 0, bf16, stream);
+        e = launch_rpe_dtable_band(ds_ws, w.ds_pitch, G, p->H, p->M, p->N, rpe->lut, rpe->lut_zero, rpe->lut_len,
+                                   rpe->const_lo, rpe->const_hi, rpe->dtable, rpe->num_buckets, causal, bf16, true, stream);
         if (e != cudaSuccess) return fail_cuda(e, "rpe_dtable_band launch");
         e = launch_rpe_dtable_add_const(rpe->dtable, dconst, rpe->lut, rpe->lut_zero, rpe->lut_len, rpe->const_lo, rpe->const_hi, p->H, stream);
         if (e != cudaSuccess) return fail_cuda(e, "rpe_dtable_add_const launch");
         return 0;
     }
-    if (rpe) {
-        // dense (1, H, M, N) gradient into the workspace (sum over the batch groups), then the producer's segmented
-        // sum folds it into the (num_buckets, H) table gradient
-        void* dbias_ws = ws + w.dbias_off;
-        const int64_t dbias_strides[4] = {(int64_t)p->H * p->M * p->N, (int64_t)p->M * p->N, p->N, 1};
+    // the dense gradient: dBias itself, or (relative-position operator) a (1, H, M, N) scratch in the workspace that the
+    // producer's segmented sum folds into the (num_buckets, H) table gradient
+    void* dbias_out = rpe ? static_cast<void*>(ws + w.dbias_off) : (mode != 0 ? p->dbias : nullptr);
+    const int64_t scratch_strides[4] = {(int64_t)p->H * p->M * p->N, (int64_t)p->M * p->N, p->N, 1};
+    const int64_t* dbias_strides = rpe ? scratch_strides : p->dbias_strides;
+    const int reduce_b = rpe ? 1 : (p->bias_B == 1), reduce_h = rpe ? 0 : (p->bias_H == 1);
+    if (w.transposed) {
+        e = launch_attn_bwd_dq_convert(dq_ws, w.dq_groups, p->dq, p->dq_strides, p->B, p->H, p->M, p->D, p->sm_scale, bf16, stream);
+        if (e != cudaSuccess) return fail_cuda(e, "attn_bwd_dq_convert launch");
+        if (dbias_out) {
+            e = launch_dbias_reduce_t(ds_ws, w.ds_pitch, dbias_out, dbias_strides, G, p->H, p->M, p->N, reduce_b, reduce_h, causal, bf16, stream);
+            if (e != cudaSuccess) return fail_cuda(e, "dbias_reduce_t launch");
+        }
+    } else {
         e = launch_attn_bwd_finalize(dq_ws, w.dq_groups, p->dq, p->dq_strides, p->B, p->H, p->M, p->N, p->D, p->sm_scale, bf16,
-                                     ds_ws, w.n_pad, dbias_ws, dbias_strides, w.ds_groups > 0 ? w.ds_groups : 1,
-                                     1, 0, p->causal != 0, stream);
+                                     ds_ws, w.ds_pitch, dbias_out, dbias_strides, G, reduce_b, reduce_h, causal, stream);
         if (e != cudaSuccess) return fail_cuda(e, "attn_bwd_finalize launch");
-        e = launch_t5_bias_bwd(dbias_ws, rpe->lut, rpe->lut_zero, rpe->lut_len, nullptr, nullptr, rpe->dtable, p->H, p->M, p->N,
+    }
+    if (rpe) {
+        e = launch_t5_bias_bwd(dbias_out, rpe->lut, rpe->lut_zero, rpe->lut_len, nullptr, nullptr, rpe->dtable, p->H, p->M, p->N,
                                rpe->num_buckets, p->dtype, stream);
         if (e != cudaSuccess) return fail_cuda(e, "t5_bias_bwd launch");
         if (dconst) {
             e = launch_rpe_dtable_add_const(rpe->dtable, dconst, rpe->lut, rpe->lut_zero, rpe->lut_len, rpe->const_lo, rpe->const_hi, p->H, stream);
             if (e != cudaSuccess) return fail_cuda(e, "rpe_dtable_add_const launch");
         }
-        return 0;
     }
-    e = launch_attn_bwd_finalize(dq_ws, w.dq_groups, p->dq, p->dq_strides, p->B, p->H, p->M, p->N, p->D, p->sm_scale, bf16,
-                                 ds_ws, w.n_pad, mode != 0 ? p->dbias : nullptr, p->dbias_strides, w.ds_groups > 0 ? w.ds_groups : 1,
-                                 p->bias_B == 1, p->bias_H == 1, p->causal != 0, stream);
-    if (e != cudaSuccess) return fail_cuda(e, "attn_bwd_finalize launch");
     return 0;
 }
 

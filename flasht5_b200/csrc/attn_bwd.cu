@@ -812,32 +812,135 @@ static cudaError_t launch_bwd_d(const AttnBwdKernelParams& kp, int bias_mode, bo
         case 3: return launch_bwd_inst<kD, kBf16, 1, true>(kp, stream);
         case 4: return launch_bwd_inst<kD, kBf16, 2, false>(kp, stream);
         case 5: return launch_bwd_inst<kD, kBf16, 2, true>(kp, stream);
-        default: break;
-    }
-    // bias mode 3 is only instantiated where this kernel is the production path (D = 128)
-    if constexpr (kD == 128) {
-        if (bias_mode == 3)
-            return causal ? launch_bwd_inst<kD, kBf16, 3, true>(kp, stream) : launch_bwd_inst<kD, kBf16, 3, false>(kp, stream);
-    }
-    return cudaErrorInvalidValue;
-}
-
-cudaError_t launch_attn_bwd(const AttnBwdKernelParams& kp, int D, bool bf16, int bias_mode, bool causal,
-                            cudaStream_t stream) {
-    static const bool force_v1 = getenv("B200T5_DEBUG_BWD_V1") != nullptr;
-    if (D <= 64 && !force_v1) return launch_attn_bwd_v2(kp, D, bf16, bias_mode, causal, stream);
-#define B200T5_BWD_CASE(DD)                                                              \
-    case DD:                                                                             \
-        return bf16 ? launch_bwd_d<DD, true>(kp, bias_mode, causal, stream)              \
-                    : launch_bwd_d<DD, false>(kp, bias_mode, causal, stream);
-    switch (D) {
-        B200T5_BWD_CASE(16)
-        B200T5_BWD_CASE(32)
-        B200T5_BWD_CASE(64)
-        B200T5_BWD_CASE(128)
+        case 6: return launch_bwd_inst<kD, kBf16, 3, false>(kp, stream);
+        case 7: return launch_bwd_inst<kD, kBf16, 3, true>(kp, stream);
         default: return cudaErrorInvalidValue;
     }
-#undef B200T5_BWD_CASE
+}
+
+// This kernel is the D = 128 path only (its TMEM budget is what forces the simpler schedule); head dims 16 / 32 / 64 take
+// the transposed-formulation kernel of attn_bwd_v3.cu.
+cudaError_t launch_attn_bwd(const AttnBwdKernelParams& kp, int D, bool bf16, int bias_mode, bool causal,
+                            cudaStream_t stream) {
+    if (D != 128) return cudaErrorInvalidValue;
+    return bf16 ? launch_bwd_d<128, true>(kp, bias_mode, causal, stream) : launch_bwd_d<128, false>(kp, bias_mode, causal, stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// helpers of the transposed-formulation kernel (attn_bwd_v3.cu)
+// ------------------------------------------------------------------------------------------
+// bias_t[bh, n, m] = bias[bh, m, n]: 64 x 64 tiles through shared memory, 16-bit elements, arbitrary input strides.
+__global__ void __launch_bounds__(256) bias_transpose_kernel(const uint16_t* __restrict__ in, int64_t s_b, int64_t s_h, int64_t s_m,
+                                                             int64_t s_n, uint16_t* __restrict__ out, int Hb, int M, int N,
+                                                             int m_pitch) {
+    __shared__ uint16_t tile[64][66];
+    const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+    const int bh = blockIdx.z, bb = bh / Hb, hb = bh % Hb;
+    const int ty = threadIdx.x >> 5, tx = threadIdx.x & 31;
+    const uint16_t* src = in + bb * s_b + hb * s_h;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int ml = ty + 8 * j, m = m0 + ml;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int nl = tx + 32 * e, n = n0 + nl;
+            tile[ml][nl] = (m < M && n < N) ? __ldg(src + (int64_t)m * s_m + (int64_t)n * s_n) : (uint16_t)0;
+        }
+    }
+    __syncthreads();
+    uint16_t* dst = out + (int64_t)bh * N * m_pitch;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int nl = ty + 8 * j, n = n0 + nl;
+        const int m = m0 + 2 * tx;
+        if (n < N && m < m_pitch) {
+            const uint32_t v = (uint32_t)tile[2 * tx][nl] | ((uint32_t)tile[2 * tx + 1][nl] << 16);
+            *reinterpret_cast<uint32_t*>(dst + (int64_t)n * m_pitch + m) = v;      // m_pitch and m are even: 4-byte aligned
+        }
+    }
+}
+
+cudaError_t launch_bias_transpose(const void* bias, const int64_t* s, void* bias_t, int Bb, int Hb, int M, int N, int m_pitch,
+                                  cudaStream_t stream) {
+    const dim3 grid((M + 63) / 64, (N + 63) / 64, Bb * Hb);
+    if (grid.y > 65535 || grid.z > 65535) return cudaErrorInvalidValue;
+    bias_transpose_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(bias), s[0], s[1], s[2], s[3],
+                                                    static_cast<uint16_t*>(bias_t), Hb, M, N, m_pitch);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// dbias[ob, oh, m, n] = sum over the reduced group / head slices of ds_t[g, h, n, m]; fp32 accumulation, one rounding.
+// 64 x 64 tiles: read rows of the transposed surface (m contiguous), transpose through shared memory, write rows of dbias.
+template <bool kBf16>
+__global__ void __launch_bounds__(256) dbias_reduce_t_kernel(const uint16_t* __restrict__ ws, int m_pitch, uint16_t* __restrict__ out,
+                                                             int64_t o_sb, int64_t o_sh, int64_t o_sm, int64_t o_sn, int G, int H,
+                                                             int M, int N, int reduce_b, int reduce_h, int causal) {
+    __shared__ float tile[64][65];
+    const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+    const int oh_n = reduce_h ? 1 : H;
+    const int ob = blockIdx.z / oh_n, oh = blockIdx.z % oh_n;
+    const int ty = threadIdx.x >> 5, tx = threadIdx.x & 31;
+    const int pseq = N - M;
+    const bool tile_masked = causal && (n0 > m0 + 63 + pseq);              // every (m, n) of the tile is above the diagonal
+    float acc[8][2];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = 0.f;
+    if (!tile_masked) {
+        const int g0 = reduce_b ? 0 : ob, g1 = reduce_b ? G : ob + 1;
+        const int h0 = reduce_h ? 0 : oh, h1 = reduce_h ? H : oh + 1;
+        const int m = m0 + 2 * tx;
+        for (int g = g0; g < g1; ++g)
+            for (int hh = h0; hh < h1; ++hh) {
+                const uint16_t* src = ws + ((int64_t)g * H + hh) * (int64_t)N * m_pitch;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int n = n0 + ty + 8 * j;
+                    if (n < N && m < M) {
+                        const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(src + (int64_t)n * m_pitch + m));
+                        const float2 f = unpack2<kBf16>(u);
+                        acc[j][0] += f.x;
+                        acc[j][1] += f.y;
+                    }
+                }
+            }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        tile[ty + 8 * j][2 * tx] = acc[j][0];
+        tile[ty + 8 * j][2 * tx + 1] = acc[j][1];
+    }
+    __syncthreads();
+    uint16_t* dst = out + ob * o_sb + oh * o_sh;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int ml = ty + 8 * j, m = m0 + ml;
+        if (m >= M) continue;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int nl = tx + 32 * e, n = n0 + nl;
+            if (n >= N) continue;
+            float v = tile[nl][ml];
+            if (causal && n > m + pseq) v = 0.f;                          // select, not multiply: unwritten tiles may hold anything
+            const uint32_t packed = pack2<kBf16>(v, 0.f);
+            dst[(int64_t)m * o_sm + (int64_t)n * o_sn] = static_cast<uint16_t>(packed & 0xFFFFu);
+        }
+    }
+}
+
+cudaError_t launch_dbias_reduce_t(const void* ds_t, int m_pitch, void* dbias, const int64_t* s, int G, int H, int M, int N,
+                                  int reduce_b, int reduce_h, bool causal, bool bf16, cudaStream_t stream) {
+    const int ob = reduce_b ? 1 : G, oh = reduce_h ? 1 : H;
+    const dim3 grid((M + 63) / 64, (N + 63) / 64, ob * oh);
+    if (grid.y > 65535 || grid.z > 65535) return cudaErrorInvalidValue;
+    if (bf16)
+        dbias_reduce_t_kernel<true><<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(ds_t), m_pitch, static_cast<uint16_t*>(dbias),
+                                                              s[0], s[1], s[2], s[3], G, H, M, N, reduce_b, reduce_h, causal ? 1 : 0);
+    else
+        dbias_reduce_t_kernel<false><<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(ds_t), m_pitch, static_cast<uint16_t*>(dbias),
+                                                               s[0], s[1], s[2], s[3], G, H, M, N, reduce_b, reduce_h, causal ? 1 : 0);
+    count_launch();
+    return cudaGetLastError();
 }
 
 cudaError_t launch_attn_bwd_preprocess(const void* o, const int64_t* os, const void* dout, const int64_t* ds,

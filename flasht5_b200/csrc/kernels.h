@@ -48,7 +48,13 @@ struct AttnBwdKernelParams {
     CUtensorMap map_v;      // (D, N, H, B)
     CUtensorMap map_do;     // (D, M, H, B)
     CUtensorMap map_bias;   // (N, M, Hb, Bb)                                 [bias mode 1]
+                            // v3 kernel (D <= 64): the TRANSPOSED copy (M, N, Hb, Bb), box (64 queries, 128 keys)
     CUtensorMap map_ds;     // (N, M, H, B) 16-bit dS workspace, row pitch = N rounded up to 8   [bias modes 1, 2]
+                            // v3 kernel (D <= 64): the TRANSPOSED surface (M, N, H, G), row pitch = M rounded up to 8
+    const void* k;          // raw K / V pointers + element strides: the v3 kernel copies its key block into TMEM itself
+    int64_t k_sb, k_sh, k_sn;
+    const void* v;
+    int64_t v_sb, v_sh, v_sn;
     CUtensorMap map_dq;     // 16-bit dQ group surface (D, M, H, dq_groups * B), box (min(D,64), 128, 1, 1), reduce-add
     const void* bias;       // [bias mode 2]
     int64_t bias_sb, bias_sh, bias_sm, bias_sn;
@@ -74,16 +80,18 @@ struct AttnBwdKernelParams {
 
 cudaError_t launch_attn_fwd(const AttnFwdKernelParams& kp, int D, bool bf16, int bias_mode, bool causal,
                             cudaStream_t stream);
-// persistent schedule of the same forward (attn_fwd_persist.cu): 2 CTAs per SM walk the work items
-cudaError_t launch_attn_fwd_persist(const AttnFwdKernelParams& kp, int D, bool bf16, int bias_mode, bool causal,
-                                    cudaStream_t stream);
-// developer kernel (attn_fwd_pingpong.cu): two query tiles per CTA, exp phases in anti-phase; D <= 64, bias modes 0, 1, 3
-cudaError_t launch_attn_fwd_pingpong(const AttnFwdKernelParams& kp, int D, bool bf16, int bias_mode, bool causal,
-                                     cudaStream_t stream);
 cudaError_t launch_attn_bwd(const AttnBwdKernelParams& kp, int D, bool bf16, int bias_mode, bool causal,
-                            cudaStream_t stream);        // dispatches: D <= 64 -> pipelined v2 kernel, D = 128 -> v1
-cudaError_t launch_attn_bwd_v2(const AttnBwdKernelParams& kp, int D, bool bf16, int bias_mode, bool causal,
+                            cudaStream_t stream);        // the D = 128 kernel (attn_bwd.cu)
+// transposed-formulation kernel (attn_bwd_v3.cu), D <= 64, bias modes 0, 1 (through the transposed copy), 3
+cudaError_t launch_attn_bwd_v3(const AttnBwdKernelParams& kp, int D, bool bf16, int bias_mode, bool causal,
                                cudaStream_t stream);
+// biasT[bb, hb, n, m] = bias[bb, hb, m, n] (16-bit elements, arbitrary input strides, output row pitch m_pitch)
+cudaError_t launch_bias_transpose(const void* bias, const int64_t* strides, void* bias_t, int Bb, int Hb, int M, int N,
+                                  int m_pitch, cudaStream_t stream);
+// dbias[bb,hb,m,n] = sum over broadcast batch-group / head of ds_t[g,h,n,m] (the transposed surface of the v3 kernel);
+// fp32 accumulation, one rounding; causal-masked entries are written as 0 without being read
+cudaError_t launch_dbias_reduce_t(const void* ds_t, int m_pitch, void* dbias, const int64_t* dbias_strides, int G, int H,
+                                  int M, int N, int reduce_b, int reduce_h, bool causal, bool bf16, cudaStream_t stream);
 
 // delta[b,h,m] = sum_d O*dO  (fp32); also zero-fills the 16-bit dQ group surface (dq_groups, B, H, M, D).
 // `zero_ptr` / `zero_bytes` (multiple of 16, may be 0): an extra surface to zero-fill in the same launch.
@@ -134,9 +142,10 @@ cudaError_t launch_rpe_band(const void* table, int64_t stride_b, int64_t stride_
                             cudaStream_t stream);
 
 // (developer path) table gradient straight from the non-constant tiles of the dS group surface; zeroes dtable first
+// `transposed`: ds_ws is the (G, H, N, M) surface of the v3 kernel (rows = keys) instead of (G, H, M, N)
 cudaError_t launch_rpe_dtable_band(const void* ds_ws, int pitch, int G, int H, int M, int N, const int32_t* lut, int lut_zero,
                                    int lut_len, int const_lo, int const_hi, float* dtable, int num_buckets, bool causal,
-                                   bool bf16, cudaStream_t stream);
+                                   bool bf16, bool transposed, cudaStream_t stream);
 // dtable[lut[const_lo + lut_zero], h] += dconst[h][0];  dtable[lut[const_hi + lut_zero], h] += dconst[h][1]
 cudaError_t launch_rpe_dtable_add_const(float* dtable, const float* dconst, const int32_t* lut, int lut_zero, int lut_len,
                                         int const_lo, int const_hi, int H, cudaStream_t stream);

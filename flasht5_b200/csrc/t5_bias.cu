@@ -355,33 +355,39 @@ cudaError_t launch_rpe_band(const void* table, int64_t stride_b, int64_t stride_
 // the rows: lanes read consecutive 16-bit elements; a wrapped diagonal is two true diagonals (d = w and d = w - 128).
 // ------------------------------------------------------------------------------------------
 template <bool kBf16>
-__global__ void __launch_bounds__(256) rpe_dtable_band_kernel(const uint16_t* __restrict__ ws, int pitch, int G, int H, int M,
-                                                              int N, const int32_t* __restrict__ lut, int lut_zero,
-                                                              int lut_len, int const_lo, int const_hi,
+__global__ void __launch_bounds__(256) rpe_dtable_band_kernel(const uint16_t* __restrict__ ws, int pitch, int G, int H, int R,
+                                                              int Cn, int pseq, int sign, const int32_t* __restrict__ lut,
+                                                              int lut_zero, int lut_len, int const_lo, int const_hi,
                                                               float* __restrict__ dtable, int num_buckets, int causal) {
+    // The surface holds one (R x Cn) matrix per (group, head): rows = queries, columns = keys (sign = +1) or the transposed
+    // surface of the v3 attention kernel, rows = keys, columns = queries (sign = -1).  Relative position of element
+    // (row0 + r, col0 + c): rel = n - m = sign * (col0 - row0 + (c - r)).
     const int col0 = blockIdx.x * 128, row0 = blockIdx.y * 128;
     const int h = blockIdx.z / G, g = blockIdx.z % G;
-    const int rel_min = col0 - row0 - 127, rel_max = col0 - row0 + 127;
+    const int base = col0 - row0;
+    const int rel_min = sign > 0 ? base - 127 : -(base + 127), rel_max = sign > 0 ? base + 127 : -(base - 127);
     if (rel_max <= const_lo || rel_min >= const_hi) return;        // constant tile: summed inside the attention kernel
-    if (causal && col0 > row0 + 127 + (N - M)) return;             // entirely masked: never written, reads as zero
+    if (causal) {                                                  // entirely masked (n > m + pseq everywhere): never written
+        if (sign > 0 ? (col0 > row0 + 127 + pseq) : (row0 > col0 + 127 + pseq)) return;
+    }
     __shared__ float sdiag[256];                                    // index d + 128, d = c - r in [-127, 127]
     __shared__ float sbucket[kMaxBuckets];
     sdiag[threadIdx.x] = 0.f;
     for (int i = threadIdx.x; i < num_buckets; i += 256) sbucket[i] = 0.f;
     __syncthreads();
     const int w = threadIdx.x & 127, half = threadIdx.x >> 7;
-    const uint16_t* base = ws + ((int64_t)g * H + h) * (int64_t)M * pitch;
+    const uint16_t* src = ws + ((int64_t)g * H + h) * (int64_t)R * pitch;
     float s_pos = 0.f, s_neg = 0.f;
 #pragma unroll 8
     for (int rr = 0; rr < 64; ++rr) {
         const int r = half * 64 + rr;
-        const int m = row0 + r;
+        const int row = row0 + r;
         int c = r + w;
         const bool wrapped = c >= 128;
         c &= 127;
-        const int n = col0 + c;
-        if (m < M && n < N) {
-            const float v = to_float16bit<kBf16>(__ldg(base + (int64_t)m * pitch + n));
+        const int col = col0 + c;
+        if (row < R && col < Cn) {
+            const float v = to_float16bit<kBf16>(__ldg(src + (int64_t)row * pitch + col));
             if (wrapped) s_neg += v;
             else s_pos += v;
         }
@@ -393,7 +399,7 @@ __global__ void __launch_bounds__(256) rpe_dtable_band_kernel(const uint16_t* __
         const int d = static_cast<int>(threadIdx.x) - 128;
         const float v = sdiag[threadIdx.x];
         if (v != 0.f) {
-            int idx = col0 - row0 + d + lut_zero;
+            int idx = sign * (base + d) + lut_zero;
             idx = idx < 0 ? 0 : (idx >= lut_len ? lut_len - 1 : idx);
             atomicAdd(&sbucket[__ldg(lut + idx)], v);
         }
@@ -407,18 +413,19 @@ __global__ void __launch_bounds__(256) rpe_dtable_band_kernel(const uint16_t* __
 
 cudaError_t launch_rpe_dtable_band(const void* ds_ws, int pitch, int G, int H, int M, int N, const int32_t* lut, int lut_zero,
                                    int lut_len, int const_lo, int const_hi, float* dtable, int num_buckets, bool causal,
-                                   bool bf16, cudaStream_t stream) {
+                                   bool bf16, bool transposed, cudaStream_t stream) {
     if (num_buckets > kMaxBuckets) return cudaErrorInvalidValue;
     cudaError_t e = cudaMemsetAsync(dtable, 0, (size_t)num_buckets * H * sizeof(float), stream);
     if (e != cudaSuccess) return e;
-    const dim3 grid((N + 127) / 128, (M + 127) / 128, H * G);
+    const int R = transposed ? N : M, Cn = transposed ? M : N;
+    const dim3 grid((Cn + 127) / 128, (R + 127) / 128, H * G);
     if (grid.y > 65535 || grid.z > 65535) return cudaErrorInvalidValue;
     if (bf16)
-        rpe_dtable_band_kernel<true><<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(ds_ws), pitch, G, H, M, N, lut, lut_zero,
-                                                               lut_len, const_lo, const_hi, dtable, num_buckets, causal ? 1 : 0);
+        rpe_dtable_band_kernel<true><<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(ds_ws), pitch, G, H, R, Cn, N - M, transposed ? -1 : 1,
+                                                               lut, lut_zero, lut_len, const_lo, const_hi, dtable, num_buckets, causal ? 1 : 0);
     else
-        rpe_dtable_band_kernel<false><<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(ds_ws), pitch, G, H, M, N, lut, lut_zero,
-                                                                lut_len, const_lo, const_hi, dtable, num_buckets, causal ? 1 : 0);
+        rpe_dtable_band_kernel<false><<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(ds_ws), pitch, G, H, R, Cn, N - M, transposed ? -1 : 1,
+                                                                lut, lut_zero, lut_len, const_lo, const_hi, dtable, num_buckets, causal ? 1 : 0);
     count_launch();
     return cudaGetLastError();
 }
@@ -449,15 +456,6 @@ cudaError_t launch_t5_bias_bwd(const void* dbias, const int32_t* lut, int lut_ze
                                const int32_t* mem_pos, float* dtable, int H, int M, int N, int num_buckets, int dbias_dtype,
                                cudaStream_t stream) {
     if (num_buckets > kMaxBuckets) return cudaErrorInvalidValue;
-    {
-        // developer switch (B200T5_T5BIAS_BWD_TILES=1): the tile-parallel diagonal walk written for the in-kernel-bias backward
-        // (rpe_dtable_band_kernel, here over every tile of a dense 16-bit dBias) instead of the row-band kernel below, which
-        // measured 0.10-0.16 of the HBM roof (256 CTAs, one per SM, few bytes in flight).  Not yet run on hardware.
-        const char* v = getenv("B200T5_T5BIAS_BWD_TILES");
-        if (v && atoi(v) != 0 && ctx_pos == nullptr && mem_pos == nullptr && dbias_dtype != 2 && (M + 127) / 128 <= 65535 && H <= 65535)
-            return launch_rpe_dtable_band(dbias, N, 1, H, M, N, lut, lut_zero, lut_len, -(1 << 30), 1 << 30, dtable, num_buckets, false,
-                                          dbias_dtype == 1, stream);
-    }
     cudaError_t e = cudaMemsetAsync(dtable, 0, (size_t)num_buckets * H * sizeof(float), stream);
     if (e != cudaSuccess) return e;
     {
