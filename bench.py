@@ -175,6 +175,83 @@ def run_reference(args):
     return 0
 
 
+def bind_to_gpu_numa_node(local_rank: int):
+    """Best effort: run this process (and therefore first-touch its pinned host buffers) on the NUMA node the GPU hangs off.
+    Round 1's end-to-end leg swung 3.2x between two boxes (3.6 vs 11.3 ms per step) -- host buffers on the far socket.
+    Returns a short description for the JSON line."""
+    try:
+        out = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=10).stdout.strip()
+        bus = out.lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]                                            # sysfs uses a 4-digit PCI domain
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return "numa node unknown (single-node host or virtualised PCI)"
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return "numa node %d has no allowed cpus" % node
+        os.sched_setaffinity(0, allowed)
+        return "bound to numa node %d (%d cpus)" % (node, len(allowed))
+    except Exception as e:   # noqa: BLE001
+        return "not bound (%s)" % repr(e)[:80]
+
+
+def load_hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured copy (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:   # noqa: BLE001
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def sibling_ops(torch, dev):
+    """RMSNorm (rows = 32 x 1024, n = 512: FAT5-small) and cross-entropy + z-loss (rows = 32 768 is 2.1 GB of logits; a
+    8 192-row slice is timed) forward / backward: algorithmic bytes over CUDA-event time,
+    rotating over buffers larger than L2, against the measured HBM copy bandwidth."""
+    from flasht5_b200 import fast_rms_layernorm, cross_entropy_loss
+    hbm, hbm_src = load_hbm_peak()
+    out = {"hbm_peak_gbs": hbm, "peak_source": hbm_src}
+
+    def timed(fn, n=20):
+        for i in range(3):
+            fn(i)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(n):
+            fn(i)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    rows, n = 32 * 1024, 512
+    xs = [torch.randn(rows, n, device=dev, dtype=torch.bfloat16) for _ in range(6)]       # 6 x 33.5 MB > L2 with dy / y
+    dys = [torch.randn(rows, n, device=dev, dtype=torch.bfloat16) for _ in range(6)]
+    w = torch.ones(n, device=dev, dtype=torch.bfloat16)
+    ms = timed(lambda i: torch.ops.b200t5.rmsnorm_fwd(xs[i % 6], w, 1e-6))
+    out["rmsnorm_fwd"] = {"rows": rows, "n": n, "ms": ms, "gbs": 2 * rows * n * 2 / ms / 1e6, "frac": 2 * rows * n * 2 / ms / 1e6 / hbm}
+    y0, rstd0 = torch.ops.b200t5.rmsnorm_fwd(xs[0], w, 1e-6)
+    ms = timed(lambda i: torch.ops.b200t5.rmsnorm_bwd(dys[i % 6], xs[i % 6], w, rstd0, 1e-6))
+    out["rmsnorm_bwd"] = {"rows": rows, "n": n, "ms": ms, "gbs": 3 * rows * n * 2 / ms / 1e6, "frac": 3 * rows * n * 2 / ms / 1e6 / hbm}
+    rows, V = 8192, 32768
+    lg = [torch.randn(rows, V, device=dev, dtype=torch.bfloat16) for _ in range(2)]          # 2 x 537 MB
+    labels = torch.randint(0, V, (rows,), device=dev)
+    ms = timed(lambda i: torch.ops.b200t5.ce_fwd(lg[i % 2], labels, None, 0.0, 1.0, 1e-4, -100), n=10)
+    out["ce_fwd"] = {"rows": rows, "vocab": V, "ms": ms, "gbs": rows * V * 2 / ms / 1e6, "frac": rows * V * 2 / ms / 1e6 / hbm}
+    losses, z, lse = torch.ops.b200t5.ce_fwd(lg[0], labels, None, 0.0, 1.0, 1e-4, -100)
+    dl = torch.ones(rows, device=dev)
+    ms = timed(lambda i: torch.ops.b200t5.ce_bwd(dl, lg[i % 2], lse, labels, 0.0, 1.0, 1e-4, -100), n=10)
+    out["ce_bwd"] = {"rows": rows, "vocab": V, "ms": ms, "gbs": 2 * rows * V * 2 / ms / 1e6, "frac": 2 * rows * V * 2 / ms / 1e6 / hbm}
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
@@ -182,7 +259,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from flasht5_b200 import _cabi, flash_attention_v2_bias
-    from flasht5_b200.data_parallel import allreduce_dbias, allreduce_dbias_overlapped
+    from flasht5_b200.data_parallel import allreduce_dbias, allreduce_dbias_f32, comm_group
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -192,6 +269,7 @@ def run_ours(args):
             raise SystemExit("--gpus %d needs the torchrun launch described in the docstring" % args.gpus)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (impl ours) needs a B200: there is no CPU fallback")
+    numa_note = bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -220,13 +298,17 @@ def run_ours(args):
     def step(i):
         q, k, v, bias, do = sets[i % NSETS]
         o, L = torch.ops.b200t5.attn_bias_fwd(q, k, v, bias, False, SM_SCALE)
-        dq, dk, dv, ds = torch.ops.b200t5.attn_bias_bwd(o, do, q, k, v, bias, L, False, SM_SCALE)
         if world > 1:
-            # the one exchange of the path: dBias summed over ranks (fp32), overlapped with the next step's kernels
-            ds = allreduce_dbias_overlapped(ds, comm_stream)
+            # the one exchange of the path: the UNROUNDED fp32 dBias is summed over ranks on a side stream (NCCL capped at a
+            # few CTAs so that it does not take SMs from the attention grids it overlaps) and rounded once afterwards
+            dq, dk, dv, ds32 = torch.ops.b200t5.attn_bias_bwd_f32dbias(o, do, q, k, v, bias, L, False, SM_SCALE)
+            ds = allreduce_dbias_f32(ds32, dtype, comm_stream, dp_group)
+        else:
+            dq, dk, dv, ds = torch.ops.b200t5.attn_bias_bwd(o, do, q, k, v, bias, L, False, SM_SCALE)
         return o, dq, dk, dv, ds
 
     comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+    dp_group = comm_group(max_ctas=8) if world > 1 else None
 
     def barrier():
         if world > 1:
@@ -282,6 +364,45 @@ def run_ours(args):
             favg = sum(fwd_ms) / len(fwd_ms)
             fach = flops_fwd(B, H, S, S, D) / (favg * 1e-3) / 1e12
             roofline["fwd_kernel"] = {"achieved": fach, "frac": fach / peak, "avg_launch_ms": favg}
+
+    # ---- sustained leg: the same step loop for >= 2 s, against the SUSTAINED cuBLAS figure, with its own clock record ----
+    sustained = None
+    if not args.no_sustained:
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peak_sus = float(json.load(f)["bf16_tflops_sustained"])
+            peak_sus_src = "measured sustained (MEASURED_PEAKS.json bf16_tflops_sustained)"
+        except Exception:   # noqa: BLE001
+            peak_sus, peak_sus_src = 1400.0, "fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained)"
+        n_sus = max(args.steps, int(2200.0 / max(ms_step, 1e-3)) + 1)
+        sampler2 = ClockSampler(local_rank) if rank == 0 else None
+        if sampler2:
+            sampler2.start()
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for i in range(n_sus):
+            step(i)
+        if world > 1:
+            torch.cuda.current_stream(dev).wait_stream(comm_stream)
+        s1.record()
+        barrier()
+        ts = torch.tensor([s0.elapsed_time(s1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        sus_ms = float(ts.item()) / n_sus
+        sus_val = world * F_step / (sus_ms * 1e-3) / 1e12
+        sustained = {"value": sus_val, "unit": UNIT, "steps": n_sus, "seconds": float(ts.item()) * 1e-3, "ms_per_step": sus_ms,
+                     "peak_tflops_per_gpu": peak_sus, "peak_source": peak_sus_src, "frac_of_sustained_peak": sus_val / (world * peak_sus),
+                     "clocks": sampler2.stop() if sampler2 else None}
+
+    # ---- the two sibling ops of the path (RMSNorm, cross-entropy + z-loss) against the HBM roof: one line each ----
+    siblings = None
+    if rank == 0 and world == 1 and not args.no_siblings:
+        try:
+            siblings = sibling_ops(torch, dev)
+        except Exception as e:   # noqa: BLE001  (informational leg)
+            siblings = {"error": repr(e)[:200]}
 
     # ---- e2e: host buffers -> public autograd API -> host results, copies inside the timed region ----
     # Every step moves q,k,v,bias,dO host->device and o,dq,dk,dv,dbias device->host (pinned memory).  Copies run on
@@ -354,6 +475,7 @@ def run_ours(args):
         e2e_ms = float(tt.item()) / e2e_steps
         e2e = {"value": world * F_step / (e2e_ms * 1e-3) / 1e12, "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps,
+               "h2d_gbs": h2d / (e2e_ms * 1e-3) / 1e9, "d2h_gbs": d2h / (e2e_ms * 1e-3) / 1e9, "host_placement": numa_note,
                "api": "flasht5_b200.flash_attention_v2_bias + torch.autograd.grad; pinned host q,k,v,bias,dO in and "
                       "o,dq,dk,dv,dbias out every step, copies double-buffered on side streams"}
 
@@ -403,12 +525,14 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": WB * world, "seq_len": WS, "parallelism": "dp%d" % world,
                        "l2": "inputs rotate over %d buffer sets of 185 MB each (> 126 MB L2)" % NSETS,
-                       "exchange": "fp32 NCCL all-reduce of dBias every step on a side stream (overlaps the next step's "
-                                   "kernels; all of them complete inside the timed region)" if world > 1 else "none"},
+                       "exchange": "NCCL all-reduce of the unrounded fp32 dBias (33.5 MB) every step on a side stream through a "
+                                   "communicator capped at 8 CTAs, one rounding afterwards (overlaps the next step's kernels; "
+                                   "all of them complete inside the timed region)" if world > 1 else "none"},
             "tokens_per_s": world * B * S / (ms_step * 1e-3),
             "frac_of_peak": value / (world * peak), "peak_tflops_per_gpu": peak, "peak_source": peak_src,
             "gpu_launches": int(launches), "launches_per_step": launches / args.steps,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "rpe_path": rpe_path,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "sustained": sustained,
+            "rpe_path": rpe_path, "sibling_ops": siblings,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -424,6 +548,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sustained", action="store_true")
+    ap.add_argument("--no-siblings", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -20,12 +20,16 @@ _DTYPE_CODE = {torch.float16: F16, torch.bfloat16: BF16, torch.float32: F32}
 I64x4 = C.c_int64 * 4
 
 
+ATTN_DETERMINISTIC = 1      # b200t5_attn_params.flags (include/b200t5.h)
+ATTN_DBIAS_F32 = 2
+
+
 class AttnParams(C.Structure):
     """Mirror of `b200t5_attn_params` (include/b200t5.h)."""
     _fields_ = [
         ("B", C.c_int32), ("H", C.c_int32), ("M", C.c_int32), ("N", C.c_int32), ("D", C.c_int32),
         ("dtype", C.c_int32), ("causal", C.c_int32), ("bias_B", C.c_int32), ("bias_H", C.c_int32),
-        ("sm_scale", C.c_float), ("device", C.c_int32), ("reserved0", C.c_int32),
+        ("sm_scale", C.c_float), ("device", C.c_int32), ("flags", C.c_int32),
         ("stream", C.c_void_p),
         ("q", C.c_void_p), ("q_strides", I64x4),
         ("k", C.c_void_p), ("k_strides", I64x4),

@@ -151,7 +151,8 @@ static int make_map_4d(CUtensorMap* map, const void* base, int elem_bytes, CUten
     uint64_t natural = d0 * static_cast<uint64_t>(elem_bytes);
     for (int i = 0; i < 3; ++i) {
         uint64_t sb = static_cast<uint64_t>(es[i]) * elem_bytes;
-        if (dims[i + 1] == 1 || es[i] <= 0) sb = (natural + 15) / 16 * 16;   // never dereferenced beyond index 0
+        if (dims[i + 1] == 1) sb = (natural + 15) / 16 * 16;                  // never dereferenced beyond index 0
+        else if (es[i] <= 0) return fail(B200T5_ERR_INVALID, "%s: stride %d is %lld for a dimension of size %llu (broadcast views must be materialised or given as a size-1 dimension)", what, i + 1, (long long)es[i], (unsigned long long)dims[i + 1]);
         if (sb % 16 != 0) return fail(B200T5_ERR_INVALID, "%s: stride %d (%lld elements) is not 16-byte aligned", what, i + 1, (long long)es[i]);
         strides[i] = sb;
         natural = sb * dims[i + 1];
@@ -172,9 +173,10 @@ static int make_map_4d(CUtensorMap* map, const void* base, int elem_bytes, CUten
 static bool strides_tma_ok(const void* ptr, const int64_t* s, int b_dim, int h_dim) {
     if (reinterpret_cast<uintptr_t>(ptr) % 16 != 0) return false;
     if (s[3] != 1) return false;
-    if (s[2] % 8 != 0) return false;
-    if (h_dim > 1 && s[1] % 8 != 0) return false;
-    if (b_dim > 1 && s[0] % 8 != 0) return false;
+    // a stride of 0 (an expanded view) on a dimension larger than 1 cannot be expressed in a tensor map
+    if (s[2] % 8 != 0 || s[2] <= 0) return false;
+    if (h_dim > 1 && (s[1] % 8 != 0 || s[1] <= 0)) return false;
+    if (b_dim > 1 && (s[0] % 8 != 0 || s[0] <= 0)) return false;
     return true;
 }
 
@@ -324,11 +326,15 @@ BwdWorkspace bwd_workspace_layout(const b200t5_attn_params* p, bool has_rpe = fa
     w.transposed = p->D <= 64;
     w.ds_pitch = w.transposed ? round_up8(p->M) : round_up8(p->N);
     w.delta_off = 0;
-    w.dq_off = align(rows * sizeof(float));
+    // D = 128: delta (B, H, M).  v3 kernel: -L * log2e and -delta, each (B, H, M rounded up to 128)
+    const size_t m_pad = (size_t)(p->M + 127) / 128 * 128;
+    w.dq_off = w.transposed ? 2 * align((size_t)p->B * p->H * m_pad * sizeof(float)) : align(rows * sizeof(float));
     // dQ group surface: <= 4 key blocks accumulate (16-bit, at L2) into one group; <= 8 groups
     const int nnb = (p->N + 127) / 128;
+    const bool deterministic = (p->flags & B200T5_ATTN_DETERMINISTIC) != 0;
     int gq = (nnb + 3) / 4;
     if (gq > 8) gq = 8;
+    if (deterministic) gq = nnb;           // one key block per group: a single addend per slot, summed in fixed order later
     w.dq_groups = gq;
     w.ds_off = w.dq_off + align((size_t)gq * rows * p->D * 2);
     // dS surface: per-batch bias -> one slice per batch (plain stores); batch-broadcast bias -> the batch is
@@ -344,6 +350,7 @@ BwdWorkspace bwd_workspace_layout(const b200t5_attn_params* p, bool has_rpe = fa
         if (((has_rpe || p->bias_B == 1) && p->B > 1) || rpe_skip) {
             int g = (p->B + 7) / 8;
             if (g > 16) g = 16;
+            if (deterministic) g = p->B;   // one batch element per group (still zero-filled + reduce-added: unwritten tiles)
             w.ds_groups = g;
             w.ds_use_reduce = 1;
         } else {
@@ -353,7 +360,8 @@ BwdWorkspace bwd_workspace_layout(const b200t5_attn_params* p, bool has_rpe = fa
     }
     w.ds_bytes = ds_bytes;
     w.bias_t_off = w.ds_off + align(ds_bytes);
-    const size_t bias_t_bytes = (w.transposed && p->bias) ? (size_t)p->bias_B * p->bias_H * (size_t)p->N * (size_t)w.ds_pitch * 2 : 0;
+    // repacked dense bias of the v3 kernel: [bias_B][bias_H][key blocks of 128][query blocks of 32][4][128][8] 16-bit
+    const size_t bias_t_bytes = (w.transposed && p->bias) ? (size_t)p->bias_B * p->bias_H * (size_t)((p->N + 127) / 128) * (size_t)(4 * ((p->M + 127) / 128)) * 4 * 128 * 16 : 0;   // whole 128-query tiles: the kernel reads every sub-tile of its last tile
     w.dbias_off = w.bias_t_off + align(bias_t_bytes);
     const bool dense_scratch = has_rpe && !(w.transposed && rpe_skip && rpe_skip_const_level() >= 2);
     w.dconst_off = w.dbias_off + (dense_scratch ? align((size_t)p->H * p->M * (size_t)p->N * 2) : 0);
@@ -386,6 +394,7 @@ static int attn_bwd_impl(const b200t5_attn_params* p, const b200t5_rpe_params* r
     if (!strides_tma_ok(p->dout, p->do_strides, p->B, p->H) || !strides_tma_ok(p->dq, p->dq_strides, p->B, p->H) ||
         !strides_tma_ok(p->dk, p->dk_strides, p->B, p->H) || !strides_tma_ok(p->dv, p->dv_strides, p->B, p->H))
         return fail(B200T5_ERR_INVALID, "dout, dq, dk, dv need unit last stride, 16-byte aligned base and other strides that are multiples of 8 elements");
+    if ((p->flags & B200T5_ATTN_DBIAS_F32) && (p->D > 64 || rpe)) return fail(B200T5_ERR_UNSUPPORTED, "B200T5_ATTN_DBIAS_F32 is implemented for head dims 16 / 32 / 64 of the dense-bias operator");
     const bool rpe_skip = rpe != nullptr && rpe_skip_const_enabled() && p->D <= 64;   // the D = 128 kernel stores every tile
     const BwdWorkspace w = bwd_workspace_layout(p, rpe != nullptr, rpe_skip);
     if (!p->workspace || p->workspace_bytes < w.total) return fail(B200T5_ERR_WORKSPACE, "workspace of %zu bytes needed, %zu given", w.total, p->workspace ? p->workspace_bytes : (size_t)0);
@@ -403,19 +412,30 @@ static int attn_bwd_impl(const b200t5_attn_params* p, const b200t5_rpe_params* r
     void* ds_ws = ws + w.ds_off;
     const int G = w.ds_groups > 0 ? w.ds_groups : 1;
 
-    // delta, zero-fill of the dQ group surface and (when dS is reduce-added) of the dS group surface: one launch
-    cudaError_t e = launch_attn_bwd_preprocess(p->o, p->o_strides, p->dout, p->do_strides, delta, dq_ws, w.dq_groups, p->B, p->H, p->M, p->D, bf16,
-                                               w.ds_use_reduce ? ds_ws : nullptr, w.ds_use_reduce ? (w.ds_bytes + 15) / 16 * 16 : 0, stream);
+    // delta, zero-fill of the dQ group surface and (when dS is reduce-added) of the dS group surface -- and, for the v3 kernel
+    // with a dense bias, the repacked bias copy -- in one launch
+    const int m_pad = (p->M + 127) / 128 * 128;
+    float* nl = delta;                                                              // v3: [nl | ndelta]
+    float* ndelta = reinterpret_cast<float*>(ws + w.dq_off / 2);
+    cudaError_t e;
+    if (w.transposed)
+        e = launch_attn_bwd_pre_fused(p->o, p->o_strides, p->dout, p->do_strides, p->lse, nl, ndelta, m_pad, dq_ws, w.dq_groups, p->B, p->H, p->M,
+                                      p->N, p->D, bf16, w.ds_use_reduce ? ds_ws : nullptr, w.ds_use_reduce ? (w.ds_bytes + 15) / 16 * 16 : 0,
+                                      rpe ? nullptr : p->bias, p->bias_strides, ws + w.bias_t_off, p->bias_B, p->bias_H, stream);
+    else
+        e = launch_attn_bwd_preprocess(p->o, p->o_strides, p->dout, p->do_strides, delta, dq_ws, w.dq_groups, p->B, p->H, p->M, p->D, bf16,
+                                       w.ds_use_reduce ? ds_ws : nullptr, w.ds_use_reduce ? (w.ds_bytes + 15) / 16 * 16 : 0, stream);
     if (e != cudaSuccess) return fail_cuda(e, "attn_bwd_preprocess launch");
 
     const CUtensorMapDataType dt = bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     const uint32_t boxd = p->D >= 64 ? 64 : p->D;
     AttnBwdKernelParams kp;
     memset(&kp, 0, sizeof(kp));
-    if ((rc = make_map_4d(&kp.map_q, p->q, 2, dt, p->D, p->M, p->H, p->B, p->q_strides[2], p->q_strides[1], p->q_strides[0], boxd, 128, "q"))) return rc;
+    const uint32_t qrows = w.transposed ? 32 : 128;         // the v3 kernel loads Q / dO per 32-query sub-tile
+    if ((rc = make_map_4d(&kp.map_q, p->q, 2, dt, p->D, p->M, p->H, p->B, p->q_strides[2], p->q_strides[1], p->q_strides[0], boxd, qrows, "q"))) return rc;
     if ((rc = make_map_4d(&kp.map_k, p->k, 2, dt, p->D, p->N, p->H, p->B, p->k_strides[2], p->k_strides[1], p->k_strides[0], boxd, 128, "k"))) return rc;
     if ((rc = make_map_4d(&kp.map_v, p->v, 2, dt, p->D, p->N, p->H, p->B, p->v_strides[2], p->v_strides[1], p->v_strides[0], boxd, 128, "v"))) return rc;
-    if ((rc = make_map_4d(&kp.map_do, p->dout, 2, dt, p->D, p->M, p->H, p->B, p->do_strides[2], p->do_strides[1], p->do_strides[0], boxd, 128, "dout"))) return rc;
+    if ((rc = make_map_4d(&kp.map_do, p->dout, 2, dt, p->D, p->M, p->H, p->B, p->do_strides[2], p->do_strides[1], p->do_strides[0], boxd, qrows, "dout"))) return rc;
     if ((rc = make_map_4d(&kp.map_dq, dq_ws, 2, dt, p->D, p->M, p->H, (uint64_t)w.dq_groups * p->B, p->D, (int64_t)p->M * p->D, (int64_t)p->H * p->M * p->D, boxd, 128, "dq group surface", true))) return rc;
     kp.dq_groups = w.dq_groups;
     // D <= 64: every dense bias goes through the transposed copy (which also absorbs unaligned rows); D = 128: TMA or pointers
@@ -431,14 +451,9 @@ static int attn_bwd_impl(const b200t5_attn_params* p, const b200t5_rpe_params* r
         }
     }
     if (w.transposed) {
-        if (mode == 1) {
-            void* bias_t = ws + w.bias_t_off;
-            e = launch_bias_transpose(p->bias, p->bias_strides, bias_t, p->bias_B, p->bias_H, p->M, p->N, w.ds_pitch, stream);
-            if (e != cudaSuccess) return fail_cuda(e, "bias_transpose launch");
-            if ((rc = make_map_4d(&kp.map_bias, bias_t, 2, dt, p->M, p->N, p->bias_H, p->bias_B, w.ds_pitch, (int64_t)p->N * w.ds_pitch, (int64_t)p->bias_H * p->N * w.ds_pitch, 64, 128, "transposed bias"))) return rc;
-        }
+        if (mode == 1) kp.bias = ws + w.bias_t_off;          // the repacked copy written by the fused pre-kernel above
         if (mode != 0) {
-            if ((rc = make_map_4d(&kp.map_ds, ds_ws, 2, dt, p->M, p->N, p->H, G, w.ds_pitch, (int64_t)p->N * w.ds_pitch, (int64_t)p->H * p->N * w.ds_pitch, 64, 128, "dS workspace (transposed)"))) return rc;
+            if ((rc = make_map_4d(&kp.map_ds, ds_ws, 2, dt, p->M, p->N, p->H, G, w.ds_pitch, (int64_t)p->N * w.ds_pitch, (int64_t)p->H * p->N * w.ds_pitch, 32, 128, "dS workspace (transposed)"))) return rc;
         }
         kp.k = p->k; kp.k_sb = p->k_strides[0]; kp.k_sh = p->k_strides[1]; kp.k_sn = p->k_strides[2];
         kp.v = p->v; kp.v_sb = p->v_strides[0]; kp.v_sh = p->v_strides[1]; kp.v_sn = p->v_strides[2];
@@ -463,6 +478,9 @@ static int attn_bwd_impl(const b200t5_attn_params* p, const b200t5_rpe_params* r
     kp.dv = p->dv; kp.dv_sb = p->dv_strides[0]; kp.dv_sh = p->dv_strides[1]; kp.dv_sn = p->dv_strides[2];
     kp.lse = p->lse;
     kp.delta = delta;
+    kp.nl = nl;
+    kp.ndelta = ndelta;
+    kp.m_pad = m_pad;
     kp.B = p->B; kp.H = p->H; kp.M = p->M; kp.N = p->N;
     kp.num_m_blocks = (p->M + 127) / 128;
     kp.num_n_blocks = (p->N + 127) / 128;
@@ -493,12 +511,10 @@ static int attn_bwd_impl(const b200t5_attn_params* p, const b200t5_rpe_params* r
     const int64_t* dbias_strides = rpe ? scratch_strides : p->dbias_strides;
     const int reduce_b = rpe ? 1 : (p->bias_B == 1), reduce_h = rpe ? 0 : (p->bias_H == 1);
     if (w.transposed) {
-        e = launch_attn_bwd_dq_convert(dq_ws, w.dq_groups, p->dq, p->dq_strides, p->B, p->H, p->M, p->D, p->sm_scale, bf16, stream);
-        if (e != cudaSuccess) return fail_cuda(e, "attn_bwd_dq_convert launch");
-        if (dbias_out) {
-            e = launch_dbias_reduce_t(ds_ws, w.ds_pitch, dbias_out, dbias_strides, G, p->H, p->M, p->N, reduce_b, reduce_h, causal, bf16, stream);
-            if (e != cudaSuccess) return fail_cuda(e, "dbias_reduce_t launch");
-        }
+        e = launch_attn_bwd_post_fused(dq_ws, w.dq_groups, p->dq, p->dq_strides, p->B, p->H, p->M, p->N, p->D, p->sm_scale, bf16, ds_ws,
+                                       w.ds_pitch, dbias_out, dbias_strides, G, reduce_b, reduce_h, causal,
+                                       !rpe && (p->flags & B200T5_ATTN_DBIAS_F32) != 0, stream);
+        if (e != cudaSuccess) return fail_cuda(e, "attn_bwd finalize launch");
     } else {
         e = launch_attn_bwd_finalize(dq_ws, w.dq_groups, p->dq, p->dq_strides, p->B, p->H, p->M, p->N, p->D, p->sm_scale, bf16,
                                      ds_ws, w.ds_pitch, dbias_out, dbias_strides, G, reduce_b, reduce_h, causal, stream);

@@ -339,7 +339,7 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdKernelParams p) {
                 const int64_t ri = ((int64_t)b * p.H + h) * p.M + grow;
                 const float Lv = __ldg(p.lse + ri);
                 dlt = __ldg(p.delta + ri);
-                L_log2 = (Lv == -INFINITY) ? INFINITY : Lv * kLog2e;   // rows with no visible key: P = 0
+                L_log2 = (Lv < -1e37f) ? INFINITY : Lv * kLog2e;   // no visible key, or every key carries the finfo.min mask: P = 0
             }
             int lim = p.N - col0 - wg * 64;                  // first masked column, relative to my half
             if (kCausal) {
@@ -551,13 +551,18 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdKernelParams p) {
 // ------------------------------------------------------------------------------------------
 // delta = rowsum(O * dO) in fp32 (reference: _bwd_preprocess :516-556) + zero the 16-bit dQ group surface.
 template <int kD, bool kBf16>
-__global__ void attn_bwd_preprocess_kernel(const uint8_t* __restrict__ o, int64_t o_sb, int64_t o_sh, int64_t o_sm,
-                                           const uint8_t* __restrict__ dout, int64_t do_sb, int64_t do_sh,
-                                           int64_t do_sm, float* __restrict__ delta, uint4* __restrict__ dq_ws,
-                                           int dq_groups, int B, int H, int M, uint4* __restrict__ zero_ptr,
-                                           int64_t zero_chunks) {
+__device__ __forceinline__ void attn_bwd_preprocess_body(const uint8_t* __restrict__ o, int64_t o_sb, int64_t o_sh, int64_t o_sm,
+                                                         const uint8_t* __restrict__ dout, int64_t do_sb, int64_t do_sh,
+                                                         int64_t do_sm, float* __restrict__ delta, uint4* __restrict__ dq_ws,
+                                                         int dq_groups, int B, int H, int M, uint4* __restrict__ zero_ptr,
+                                                         int64_t zero_chunks, int vblock, int vgrid,
+                                                         const float* __restrict__ lse = nullptr, float* __restrict__ nl_out = nullptr,
+                                                         int m_pad = 0) {
+    // nl_out != NULL (v3 kernel): the row statistics are written in the form the kernel consumes, in rows padded to m_pad
+    // (a multiple of 128) entries:  nl = -L * log2e (-inf for a row without visible key, for a row whose every key carries
+    // the finfo.min mask, and for the padding), delta -> -delta (0 in the padding).
     constexpr int kTpr = kD / 8;                              // threads per row, 8 elements (16 B) each
-    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gid = (int64_t)vblock * blockDim.x + threadIdx.x;
     const int64_t row = gid / kTpr;
     const int part = static_cast<int>(gid % kTpr);
     const int64_t rows = (int64_t)B * H * M;
@@ -582,16 +587,44 @@ __global__ void attn_bwd_preprocess_kernel(const uint8_t* __restrict__ o, int64_
     }
 #pragma unroll
     for (int off = kTpr / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (row < rows && part == 0) delta[row] = acc;
+    if (row < rows && part == 0) {
+        if (nl_out == nullptr) {
+            delta[row] = acc;
+        } else {
+            const int64_t prow = (row / M) * m_pad + (row % M);
+            const float Lv = __ldg(lse + row);
+            nl_out[prow] = Lv < -1e37f ? -INFINITY : -Lv * 1.4426950408889634f;
+            delta[prow] = -acc;
+        }
+    }
+    if (nl_out != nullptr && m_pad > M) {
+        const int64_t pad = m_pad - M, total = (int64_t)B * H * pad;
+        for (int64_t i = gid; i < total; i += (int64_t)vgrid * blockDim.x) {
+            const int64_t prow = (i / pad) * m_pad + M + (i % pad);
+            nl_out[prow] = -INFINITY;
+            delta[prow] = 0.f;
+        }
+    }
     // zero-fill of the dS batch-group surface (replaces a separate memset node)
-    for (int64_t i = gid; i < zero_chunks; i += (int64_t)gridDim.x * blockDim.x) zero_ptr[i] = make_uint4(0, 0, 0, 0);
+    for (int64_t i = gid; i < zero_chunks; i += (int64_t)vgrid * blockDim.x) zero_ptr[i] = make_uint4(0, 0, 0, 0);
 }
 
 template <int kD, bool kBf16>
-__global__ void attn_bwd_dq_convert_kernel(const uint4* __restrict__ dq_ws, int dq_groups, uint8_t* __restrict__ dq,
-                                           int64_t sb, int64_t sh, int64_t sm, int B, int H, int M, float scale) {
+__global__ void attn_bwd_preprocess_kernel(const uint8_t* __restrict__ o, int64_t o_sb, int64_t o_sh, int64_t o_sm,
+                                           const uint8_t* __restrict__ dout, int64_t do_sb, int64_t do_sh,
+                                           int64_t do_sm, float* __restrict__ delta, uint4* __restrict__ dq_ws,
+                                           int dq_groups, int B, int H, int M, uint4* __restrict__ zero_ptr,
+                                           int64_t zero_chunks) {
+    attn_bwd_preprocess_body<kD, kBf16>(o, o_sb, o_sh, o_sm, dout, do_sb, do_sh, do_sm, delta, dq_ws, dq_groups, B, H, M, zero_ptr,
+                                        zero_chunks, blockIdx.x, gridDim.x);
+}
+
+template <int kD, bool kBf16>
+__device__ __forceinline__ void attn_bwd_dq_convert_body(const uint4* __restrict__ dq_ws, int dq_groups, uint8_t* __restrict__ dq,
+                                                         int64_t sb, int64_t sh, int64_t sm, int B, int H, int M, float scale,
+                                                         int vblock) {
     constexpr int kTpr = kD / 8;
-    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gid = (int64_t)vblock * blockDim.x + threadIdx.x;
     const int64_t row = gid / kTpr;
     const int part = static_cast<int>(gid % kTpr);
     const int64_t rows = (int64_t)B * H * M;
@@ -619,6 +652,12 @@ __global__ void attn_bwd_dq_convert_kernel(const uint4* __restrict__ dq_ws, int 
     out.z = pack2<kBf16>(acc[4] * scale, acc[5] * scale);
     out.w = pack2<kBf16>(acc[6] * scale, acc[7] * scale);
     *reinterpret_cast<uint4*>(dq + 2 * (bb * sb + hh * sh + m * sm + part * 8)) = out;
+}
+
+template <int kD, bool kBf16>
+__global__ void attn_bwd_dq_convert_kernel(const uint4* __restrict__ dq_ws, int dq_groups, uint8_t* __restrict__ dq,
+                                           int64_t sb, int64_t sh, int64_t sm, int B, int H, int M, float scale) {
+    attn_bwd_dq_convert_body<kD, kBf16>(dq_ws, dq_groups, dq, sb, sh, sm, B, H, M, scale, blockIdx.x);
 }
 
 // dBias = sum of the per-(batch, head) dS tiles over every broadcast dimension, fp32 accumulation,
@@ -829,57 +868,78 @@ cudaError_t launch_attn_bwd(const AttnBwdKernelParams& kp, int D, bool bf16, int
 // ------------------------------------------------------------------------------------------
 // helpers of the transposed-formulation kernel (attn_bwd_v3.cu)
 // ------------------------------------------------------------------------------------------
-// bias_t[bh, n, m] = bias[bh, m, n]: 64 x 64 tiles through shared memory, 16-bit elements, arbitrary input strides.
-__global__ void __launch_bounds__(256) bias_transpose_kernel(const uint16_t* __restrict__ in, int64_t s_b, int64_t s_h, int64_t s_m,
-                                                             int64_t s_n, uint16_t* __restrict__ out, int Hb, int M, int N,
-                                                             int m_pitch) {
-    __shared__ uint16_t tile[64][66];
-    const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
-    const int bh = blockIdx.z, bb = bh / Hb, hb = bh % Hb;
-    const int ty = threadIdx.x >> 5, tx = threadIdx.x & 31;
+// Repacked dense bias for the v3 kernel (see kernels.h): one block per (bh, key block, query block of 32): reads 32 rows of
+// 128 bias values (coalesced along n), writes 4 x 128 16-byte words (thread = key row order the attention kernel reads).
+__device__ __forceinline__ void bias_repack_body(const uint16_t* __restrict__ in, int64_t s_b, int64_t s_h, int64_t s_m,
+                                                 int64_t s_n, uint4* __restrict__ out, int Hb, int M, int N, int qb, int kb, int bh,
+                                                 int n_qb, int n_kb) {
+    __shared__ uint16_t tile[32][130];
+    const int bb = bh / Hb, hb = bh % Hb;
+    const int m0 = qb * 32, n0 = kb * 128;
     const uint16_t* src = in + bb * s_b + hb * s_h;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int ml = ty + 8 * j, m = m0 + ml;
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int nl = tx + 32 * e, n = n0 + nl;
-            tile[ml][nl] = (m < M && n < N) ? __ldg(src + (int64_t)m * s_m + (int64_t)n * s_n) : (uint16_t)0;
-        }
+    const int tx = threadIdx.x & 127, ty = threadIdx.x >> 7;
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+        const int ml = ty + 2 * i, m = m0 + ml, n = n0 + tx;
+        tile[ml][tx] = (m < M && n < N) ? __ldg(src + (int64_t)m * s_m + (int64_t)n * s_n) : (uint16_t)0;
     }
     __syncthreads();
-    uint16_t* dst = out + (int64_t)bh * N * m_pitch;
+    uint4* dst = out + (((int64_t)bh * n_kb + kb) * n_qb + qb) * (4 * 128);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int nl = ty + 8 * j, n = n0 + nl;
-        const int m = m0 + 2 * tx;
-        if (n < N && m < m_pitch) {
-            const uint32_t v = (uint32_t)tile[2 * tx][nl] | ((uint32_t)tile[2 * tx + 1][nl] << 16);
-            *reinterpret_cast<uint32_t*>(dst + (int64_t)n * m_pitch + m) = v;      // m_pitch and m are even: 4-byte aligned
-        }
+    for (int i = 0; i < 2; ++i) {
+        const int idx = threadIdx.x + 256 * i;          // c * 128 + n
+        const int c = idx >> 7, n = idx & 127;
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            w[e] = (uint32_t)tile[c * 8 + 2 * e][n] | ((uint32_t)tile[c * 8 + 2 * e + 1][n] << 16);
+        dst[idx] = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
 
-cudaError_t launch_bias_transpose(const void* bias, const int64_t* s, void* bias_t, int Bb, int Hb, int M, int N, int m_pitch,
-                                  cudaStream_t stream) {
-    const dim3 grid((M + 63) / 64, (N + 63) / 64, Bb * Hb);
+__global__ void __launch_bounds__(256) bias_repack_kernel(const uint16_t* __restrict__ in, int64_t s_b, int64_t s_h, int64_t s_m,
+                                                          int64_t s_n, uint4* __restrict__ out, int Hb, int M, int N) {
+    bias_repack_body(in, s_b, s_h, s_m, s_n, out, Hb, M, N, blockIdx.x, blockIdx.y, blockIdx.z, gridDim.x, gridDim.y);
+}
+
+// delta / zero-fill and the bias repack in ONE launch (independent work; block-index split)
+template <int kD, bool kBf16>
+__global__ void __launch_bounds__(256) attn_bwd_pre_fused_kernel(const uint8_t* __restrict__ o, int64_t o_sb, int64_t o_sh, int64_t o_sm,
+                                                                 const uint8_t* __restrict__ dout, int64_t do_sb, int64_t do_sh, int64_t do_sm,
+                                                                 float* __restrict__ delta, uint4* __restrict__ dq_ws, int dq_groups, int B,
+                                                                 int H, int M, uint4* __restrict__ zero_ptr, int64_t zero_chunks,
+                                                                 int pre_blocks, const uint16_t* __restrict__ bias, int64_t s_b, int64_t s_h,
+                                                                 int64_t s_m, int64_t s_n, uint4* __restrict__ bias_p, int Hb, int N,
+                                                                 int n_qb, int n_kb, const float* __restrict__ lse,
+                                                                 float* __restrict__ nl_out, int m_pad) {
+    if (static_cast<int>(blockIdx.x) < pre_blocks) {
+        attn_bwd_preprocess_body<kD, kBf16>(o, o_sb, o_sh, o_sm, dout, do_sb, do_sh, do_sm, delta, dq_ws, dq_groups, B, H, M, zero_ptr,
+                                            zero_chunks, blockIdx.x, pre_blocks, lse, nl_out, m_pad);
+        return;
+    }
+    const int id = static_cast<int>(blockIdx.x) - pre_blocks;
+    bias_repack_body(bias, s_b, s_h, s_m, s_n, bias_p, Hb, M, N, id % n_qb, (id / n_qb) % n_kb, id / (n_qb * n_kb), n_qb, n_kb);
+}
+
+cudaError_t launch_bias_repack(const void* bias, const int64_t* s, void* bias_p, int Bb, int Hb, int M, int N, cudaStream_t stream) {
+    const dim3 grid(4 * ((M + 127) / 128), (N + 127) / 128, Bb * Hb);   // whole 128-query tiles (zero beyond M)
     if (grid.y > 65535 || grid.z > 65535) return cudaErrorInvalidValue;
-    bias_transpose_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(bias), s[0], s[1], s[2], s[3],
-                                                    static_cast<uint16_t*>(bias_t), Hb, M, N, m_pitch);
+    bias_repack_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(bias), s[0], s[1], s[2], s[3], static_cast<uint4*>(bias_p),
+                                                 Hb, M, N);
     count_launch();
     return cudaGetLastError();
 }
 
 // dbias[ob, oh, m, n] = sum over the reduced group / head slices of ds_t[g, h, n, m]; fp32 accumulation, one rounding.
 // 64 x 64 tiles: read rows of the transposed surface (m contiguous), transpose through shared memory, write rows of dbias.
-template <bool kBf16>
-__global__ void __launch_bounds__(256) dbias_reduce_t_kernel(const uint16_t* __restrict__ ws, int m_pitch, uint16_t* __restrict__ out,
-                                                             int64_t o_sb, int64_t o_sh, int64_t o_sm, int64_t o_sn, int G, int H,
-                                                             int M, int N, int reduce_b, int reduce_h, int causal) {
+template <bool kBf16, bool kOutF32>
+__device__ __forceinline__ void dbias_reduce_t_body(const uint16_t* __restrict__ ws, int m_pitch, void* __restrict__ out_v,
+                                                    int64_t o_sb, int64_t o_sh, int64_t o_sm, int64_t o_sn, int G, int H,
+                                                    int M, int N, int reduce_b, int reduce_h, int causal, int bx, int by, int bz) {
     __shared__ float tile[64][65];
-    const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+    const int m0 = bx * 64, n0 = by * 64;
     const int oh_n = reduce_h ? 1 : H;
-    const int ob = blockIdx.z / oh_n, oh = blockIdx.z % oh_n;
+    const int ob = bz / oh_n, oh = bz % oh_n;
     const int ty = threadIdx.x >> 5, tx = threadIdx.x & 31;
     const int pseq = N - M;
     const bool tile_masked = causal && (n0 > m0 + 63 + pseq);              // every (m, n) of the tile is above the diagonal
@@ -911,7 +971,7 @@ __global__ void __launch_bounds__(256) dbias_reduce_t_kernel(const uint16_t* __r
         tile[ty + 8 * j][2 * tx + 1] = acc[j][1];
     }
     __syncthreads();
-    uint16_t* dst = out + ob * o_sb + oh * o_sh;
+    const int64_t obase = ob * o_sb + oh * o_sh;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int ml = ty + 8 * j, m = m0 + ml;
@@ -922,23 +982,53 @@ __global__ void __launch_bounds__(256) dbias_reduce_t_kernel(const uint16_t* __r
             if (n >= N) continue;
             float v = tile[nl][ml];
             if (causal && n > m + pseq) v = 0.f;                          // select, not multiply: unwritten tiles may hold anything
-            const uint32_t packed = pack2<kBf16>(v, 0.f);
-            dst[(int64_t)m * o_sm + (int64_t)n * o_sn] = static_cast<uint16_t>(packed & 0xFFFFu);
+            const int64_t oi = obase + (int64_t)m * o_sm + (int64_t)n * o_sn;
+            if constexpr (kOutF32) {
+                static_cast<float*>(out_v)[oi] = v;
+            } else {
+                const uint32_t packed = pack2<kBf16>(v, 0.f);
+                static_cast<uint16_t*>(out_v)[oi] = static_cast<uint16_t>(packed & 0xFFFFu);
+            }
         }
     }
 }
 
+template <bool kBf16, bool kOutF32>
+__global__ void __launch_bounds__(256) dbias_reduce_t_kernel(const uint16_t* __restrict__ ws, int m_pitch, void* __restrict__ out_v,
+                                                             int64_t o_sb, int64_t o_sh, int64_t o_sm, int64_t o_sn, int G, int H,
+                                                             int M, int N, int reduce_b, int reduce_h, int causal) {
+    dbias_reduce_t_body<kBf16, kOutF32>(ws, m_pitch, out_v, o_sb, o_sh, o_sm, o_sn, G, H, M, N, reduce_b, reduce_h, causal, blockIdx.x,
+                                        blockIdx.y, blockIdx.z);
+}
+
+// dQ conversion and the transposing dBias reduction in ONE launch (independent work; block-index split)
+template <int kD, bool kBf16, bool kOutF32>
+__global__ void __launch_bounds__(256) attn_bwd_post_fused_kernel(const uint4* __restrict__ dq_ws, int dq_groups, uint8_t* __restrict__ dq,
+                                                                  int64_t sb, int64_t sh, int64_t sm, int B, int H, int M, float scale,
+                                                                  int cvt_blocks, const uint16_t* __restrict__ ws, int m_pitch,
+                                                                  void* __restrict__ dbias, int64_t o_sb, int64_t o_sh, int64_t o_sm,
+                                                                  int64_t o_sn, int G, int N, int reduce_b, int reduce_h, int causal, int gx,
+                                                                  int gy) {
+    if (static_cast<int>(blockIdx.x) < cvt_blocks) {
+        attn_bwd_dq_convert_body<kD, kBf16>(dq_ws, dq_groups, dq, sb, sh, sm, B, H, M, scale, blockIdx.x);
+        return;
+    }
+    const int id = static_cast<int>(blockIdx.x) - cvt_blocks;
+    dbias_reduce_t_body<kBf16, kOutF32>(ws, m_pitch, dbias, o_sb, o_sh, o_sm, o_sn, G, H, M, N, reduce_b, reduce_h, causal, id % gx,
+                                        (id / gx) % gy, id / (gx * gy));
+}
+
 cudaError_t launch_dbias_reduce_t(const void* ds_t, int m_pitch, void* dbias, const int64_t* s, int G, int H, int M, int N,
-                                  int reduce_b, int reduce_h, bool causal, bool bf16, cudaStream_t stream) {
+                                  int reduce_b, int reduce_h, bool causal, bool bf16, bool out_f32, cudaStream_t stream) {
     const int ob = reduce_b ? 1 : G, oh = reduce_h ? 1 : H;
     const dim3 grid((M + 63) / 64, (N + 63) / 64, ob * oh);
     if (grid.y > 65535 || grid.z > 65535) return cudaErrorInvalidValue;
-    if (bf16)
-        dbias_reduce_t_kernel<true><<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(ds_t), m_pitch, static_cast<uint16_t*>(dbias),
-                                                              s[0], s[1], s[2], s[3], G, H, M, N, reduce_b, reduce_h, causal ? 1 : 0);
-    else
-        dbias_reduce_t_kernel<false><<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(ds_t), m_pitch, static_cast<uint16_t*>(dbias),
-                                                               s[0], s[1], s[2], s[3], G, H, M, N, reduce_b, reduce_h, causal ? 1 : 0);
+#define B200T5_DBR(BF, F32)                                                                                                   \
+    dbias_reduce_t_kernel<BF, F32><<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(ds_t), m_pitch, dbias, s[0], s[1], s[2], \
+                                                             s[3], G, H, M, N, reduce_b, reduce_h, causal ? 1 : 0)
+    if (bf16) { if (out_f32) B200T5_DBR(true, true); else B200T5_DBR(true, false); }
+    else { if (out_f32) B200T5_DBR(false, true); else B200T5_DBR(false, false); }
+#undef B200T5_DBR
     count_launch();
     return cudaGetLastError();
 }
@@ -1061,6 +1151,69 @@ cudaError_t launch_attn_bwd_finalize(const void* dq_ws, int dq_groups, void* dq,
         default: return cudaErrorInvalidValue;
     }
 #undef B200T5_FIN
+    count_launch();
+    return cudaGetLastError();
+}
+
+// v3 kernel: row statistics (-L * log2e and -delta, padded rows) + zero-fills + (bias != NULL) the bias repack in one launch
+cudaError_t launch_attn_bwd_pre_fused(const void* o, const int64_t* os, const void* dout, const int64_t* ds, const float* lse,
+                                      float* nl_out, float* ndelta_out, int m_pad, void* dq_ws, int dq_groups, int B, int H, int M,
+                                      int N, int D, bool bf16, void* zero_ptr, size_t zero_bytes, const void* bias, const int64_t* bs,
+                                      void* bias_p, int Bb, int Hb, cudaStream_t stream) {
+    const int64_t threads = (int64_t)B * H * M * (D / 8);
+    const int pre_blocks = static_cast<int>((threads + 255) / 256);
+    const int n_qb = 4 * ((M + 127) / 128), n_kb = (N + 127) / 128;
+    const int64_t rep_blocks = bias ? (int64_t)n_qb * n_kb * Bb * Hb : 0;
+    if (pre_blocks + rep_blocks > 0x7FFFFFFFLL) return cudaErrorInvalidValue;
+    const int grid = pre_blocks + static_cast<int>(rep_blocks);
+    const int64_t zero[4] = {0, 0, 0, 0};
+    if (!bias) bs = zero;
+#define B200T5_PREF(DD, BF)                                                                                                  \
+    attn_bwd_pre_fused_kernel<DD, BF><<<grid, 256, 0, stream>>>(                                                              \
+        static_cast<const uint8_t*>(o), os[0], os[1], os[2], static_cast<const uint8_t*>(dout), ds[0], ds[1], ds[2], ndelta_out, \
+        static_cast<uint4*>(dq_ws), dq_groups, B, H, M, static_cast<uint4*>(zero_ptr), static_cast<int64_t>(zero_bytes / 16), \
+        pre_blocks, static_cast<const uint16_t*>(bias), bs[0], bs[1], bs[2], bs[3], static_cast<uint4*>(bias_p), Hb, N, n_qb, n_kb, \
+        lse, nl_out, m_pad)
+    switch (D) {
+        case 16: if (bf16) B200T5_PREF(16, true); else B200T5_PREF(16, false); break;
+        case 32: if (bf16) B200T5_PREF(32, true); else B200T5_PREF(32, false); break;
+        case 64: if (bf16) B200T5_PREF(64, true); else B200T5_PREF(64, false); break;
+        default: return cudaErrorInvalidValue;
+    }
+#undef B200T5_PREF
+    count_launch();
+    return cudaGetLastError();
+}
+
+// dQ conversion + transposing dBias reduction in one launch.  dbias == nullptr: plain dQ conversion.
+cudaError_t launch_attn_bwd_post_fused(const void* dq_ws, int dq_groups, void* dq, const int64_t* dqs, int B, int H, int M, int N,
+                                       int D, float sm_scale, bool bf16, const void* ds_t, int m_pitch, void* dbias,
+                                       const int64_t* dbs, int G, int reduce_b, int reduce_h, bool causal, bool out_f32,
+                                       cudaStream_t stream) {
+    if (dbias == nullptr) return launch_attn_bwd_dq_convert(dq_ws, dq_groups, dq, dqs, B, H, M, D, sm_scale, bf16, stream);
+    const int64_t cvt_threads = (int64_t)B * H * M * (D / 8);
+    const int cvt_blocks = static_cast<int>((cvt_threads + 255) / 256);
+    const int ob = reduce_b ? 1 : G, oh = reduce_h ? 1 : H;
+    const int gx = (M + 63) / 64, gy = (N + 63) / 64;
+    const int64_t red_blocks = (int64_t)gx * gy * ob * oh;
+    if (cvt_blocks + red_blocks > 0x7FFFFFFFLL) return cudaErrorInvalidValue;
+    const int grid = cvt_blocks + static_cast<int>(red_blocks);
+#define B200T5_POSTF(DD, BF, F32)                                                                                              \
+    attn_bwd_post_fused_kernel<DD, BF, F32><<<grid, 256, 0, stream>>>(                                                          \
+        static_cast<const uint4*>(dq_ws), dq_groups, static_cast<uint8_t*>(dq), dqs[0], dqs[1], dqs[2], B, H, M, sm_scale,      \
+        cvt_blocks, static_cast<const uint16_t*>(ds_t), m_pitch, dbias, dbs[0], dbs[1], dbs[2], dbs[3], G, N, reduce_b, reduce_h, \
+        causal ? 1 : 0, gx, gy)
+#define B200T5_POSTF2(DD)                                                                            \
+    if (bf16) { if (out_f32) B200T5_POSTF(DD, true, true); else B200T5_POSTF(DD, true, false); }     \
+    else { if (out_f32) B200T5_POSTF(DD, false, true); else B200T5_POSTF(DD, false, false); }
+    switch (D) {
+        case 16: B200T5_POSTF2(16) break;
+        case 32: B200T5_POSTF2(32) break;
+        case 64: B200T5_POSTF2(64) break;
+        default: return cudaErrorInvalidValue;
+    }
+#undef B200T5_POSTF2
+#undef B200T5_POSTF
     count_launch();
     return cudaGetLastError();
 }

@@ -14,23 +14,42 @@
 // reduces into the (transposed) dBias surface.  Shared-memory traffic per tile drops from ~430 KB to ~210 KB (+96 KB
 // with a dense bias).
 //
-// One CTA = one (batch, head, 128-key block); it walks the query sequence in 128-row tiles, each processed as two
-// 64-query half tiles t = 2k, 2k+1 that alternate between two S^T / dP^T buffers in TMEM and two compute warpgroups:
+// One CTA = one (batch, head, 128-key block); it walks the query sequence in 128-row tiles, each processed as four
+// 32-query sub-tiles t = 4k + j over FOUR S^T / dP^T buffers in TMEM.  Compute warpgroup j owns buffer j (one sub-tile per
+// tile), and the MMAs are issued by two warps so that neither waits on the other's barriers:
 //
-//   tensor pipe (one thread)   S,dP(t+1) | dV,dK(t) | [dQ(k) after the second half] | S,dP(t+2) | ...
-//   compute warpgroup t & 1    wait S,dP(t) -> P, dS in registers -> P^T, dS^T -> TMEM, dS -> smem -> signal
-//   drain warpgroup            dQ(k): TMEM -> 16-bit staging tile -> TMA reduce-add into the dQ group surface
+//   MMA warps A0-A3 one per sub-tile j: wait Q / dO slot, S^T / dP^T buffer t & 1 free -> S^T(t), dP^T(t)
+//                   (four warps: a blocking barrier probe costs ~100 cycles even when the phase has long completed, and one
+//                    warp doing two or three of them per sub-tile set the pace of the whole CTA at ~550 cycles per sub-tile)
+//   compute WG j    wait S,dP(t) -> P, dS in registers -> P^T, dS^T -> TMEM, dS -> smem -> signal
+//   MMA warp B      for t: wait P,dS(t) -> dV,dK(t) -> free buffer j and the Q / dO slot
+//   warp C          for t: wait P,dS(t) -> TMA reduce-add of the dS^T box into the dBias surface;  after j = 3: dQ(k)
+//   drain WG        dQ(k): TMEM -> 16-bit staging tile -> TMA reduce-add into the dQ group surface
+// The compute warps never synchronise with each other: every thread arrives on the P,dS barrier of its buffer by itself, and
+// the row statistics come from global memory in the form the kernel consumes (written by the pre-kernel).
 //
-//   warps 0-3 / 4-7 : compute warpgroups (thread = key row)     warps 8-11 : K, V -> TMEM (prologue), dQ drain
-//   warp 12 : TMA producer K, Q / dO ring      warp 13 : tcgen05.mma issuer      warp 14 : TMA producer of the bias tiles
+// (Measured on the way here -- profiles/r2b_*: (1) two 64-query half tiles over two buffers left every warpgroup idle ~900
+//  cycles per tile, because S^T(t+2) lands in the buffer of S^T(t) and cannot be issued before dV,dK(t) consumed P^T(t);
+//  (2) four buffers with two warpgroups and one MMA warp: the warpgroup's own chain wait -> math -> tcgen05.st -> fences ->
+//  barrier (~1 100 cycles per sub-tile, of which ~500 are math) and the single MMA thread's blocking waits (~90 cycles per
+//  completed mbarrier probe) set the pace at 3 300 cycles per tile against 1 424 cycles of tensor work; tools/micro/mma_rate.cu
+//  shows TS-mode MMAs run at the ideal rate down to N = 16 while SS-mode ones are bound by the 128 B/clk shared-memory port.)
 //
-// TMEM columns: S^T [0,64) [64,128) | dP^T [128,192) [192,256) | dV [256,256+D) | dK [256+D,256+2D) |
-//               dQ [256+2D,256+3D) | K [448,448+D/2) | V [480,480+D/2)       (P^T / dS^T alias the first 32 columns of
-//               their S^T / dP^T buffer).
+//   warps 0-15  : compute warpgroups 0-3 (thread = key row)     warps 16-19 : K, V -> TMEM (prologue), dQ drain
+//   warp 20 : TMA producer K, Q / dO ring   warps 21, 24, 26, 27 : MMA warps A (S^T, dP^T of sub-tile j = 0..3 of every tile)
+//   warps 22, 25 : MMA warps B (dV, dK of even / odd sub-tiles)   warp 23 : warp C (dQ, dS out)
 //
-// Bias modes: 0 none | 1 dense bias, read through a TRANSPOSED copy (B|1, H|1, N, M) that api.cu makes in the workspace
-// (so that a thread = key row reads its bias values with 16-byte loads) | 3 T5 relative-position bias from the band.
-// dS leaves the CTA transposed as well: the surface is (G, H, N, M) and the finalize kernel transposes while it reduces.
+// TMEM columns: S^T 2 x [32] in [0,64) | dP^T 2 x [32] in [64,128) | P^T 4 x [16] in [128,192) | dS^T 4 x [16] in [192,256) |
+//               dV [256,256+D) | dK [256+D,256+2D) | dQ [256+2D,256+3D) | K [448,448+D/2) | V [480,480+D/2).
+// S^T / dP^T buffers are free again as soon as the compute warps have them in registers, so warp A refills them at once and a
+// warpgroup's next S^T never waits for the dV / dK MMAs of its previous sub-tile (with P^T aliased over S^T it did: ~1 800
+// cycles per tile, profiles/r2b_*); P^T / dS^T have their own columns, one set per warpgroup.
+//
+// Bias modes: 0 none | 1 dense bias, read from a REPACKED copy that api.cu makes in the workspace: for every (key block,
+// 32-query sub-tile) the 128 x 32 values are stored as 4 x [128 keys][8 queries], so that thread = key row fetches its 32
+// bias values with four fully coalesced 16-byte global loads, one sub-tile ahead, with no shared-memory staging at all |
+// 3 T5 relative-position bias from the band.
+// dS leaves the CTA transposed: the surface is (G, H, N, M) and the finalize kernel transposes while it reduces.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -40,8 +59,9 @@ namespace {
 
 constexpr int kBM = 128;            // queries per tile
 constexpr int kBN = 128;            // keys per CTA
-constexpr int kSub = 64;            // queries per half tile
-constexpr int kBoxBytes = 128 * 64 * 2;   // [128 keys][64 queries] 16-bit, 128B-swizzled rows
+constexpr int kSub = 32;            // queries per sub-tile
+constexpr int kNSub = kBM / kSub;   // 4
+constexpr int kBoxBytes = 128 * kSub * 2;   // [128 keys][32 queries] 16-bit, 64B-swizzled rows
 constexpr float kLog2e = 1.4426950408889634f;
 
 template <int kD>
@@ -49,25 +69,31 @@ struct Bwd3Cfg {
     static_assert(kD == 16 || kD == 32 || kD == 64, "v3 backward covers head dims 16, 32, 64");
     static constexpr int kRowBytes = kD * 2;
     static constexpr int kTileBytes = 128 * kD * 2;
-    static constexpr int kHalfTileBytes = 64 * kD * 2;
+    static constexpr int kSubTileBytes = kSub * kD * 2;
     static constexpr uint32_t kSwizzle = kRowBytes == 128 ? kSwz128 : (kRowBytes == 64 ? kSwz64 : kSwz32);
-    static constexpr int kQStages = 2;
-    static constexpr int kBiasStages = 4;
+    // Q / dO ring: one slot = the 32 query rows of one sub-tile (Q rows + dO rows).  11 slots = almost three tiles of look-ahead: a
+    // slot is released as soon as the dV / dK MMAs of its sub-tile complete, so the producer runs ~2.5 tiles ahead (a ring of
+    // two whole tiles released after dQ(k) left the first sub-tile of every other tile waiting ~2 400 cycles for its TMA)
+    static constexpr int kSlots = 11;
     static constexpr int kK = 0;
     static constexpr int kQ = kK + kTileBytes;
-    static constexpr int kDO = kQ + kQStages * kTileBytes;
-    static constexpr int kBias = kDO + kQStages * kTileBytes;          // bias ring (mode 1) or the band (mode 3)
-    static constexpr int kDS = kBias + kBiasStages * kBoxBytes;        // [2 boxes] dS^T of the current tile
-    static constexpr int kDQ = kDS + 2 * kBoxBytes;                    // dQ staging tile [128][D] io dtype
-    static constexpr int kStats = kDQ + kTileBytes;                    // [2 wg][2 buf][2][64] fp32: -L*log2e, -delta
-    static constexpr int kBars = kStats + 2 * 2 * 2 * 64 * 4;
-    static constexpr int kNumBars = 2 + 2 * kQStages + 2 * kBiasStages + 2 + 2 + 2;
+    static constexpr int kDO = kQ + kSlots * kSubTileBytes;
+    static constexpr int kDS = kDO + kSlots * kSubTileBytes;           // [2 tiles][4 boxes] dS^T
+    static constexpr int kDQ = kDS + 2 * kNSub * kBoxBytes;            // dQ staging tile [128][D] io dtype
+    static constexpr int kBand = kDQ + kTileBytes;                     // relative-position band (mode 3), <= 32 KB
+    static constexpr int kStats = kBand + 32768;                       // [kSlots][2][32] fp32: -L*log2e, -delta of the slot's queries
+    static constexpr int kBars = kStats + kSlots * 2 * kSub * 4;
+    static constexpr int kNumBars = 2 + 2 * kSlots + 6 * kNSub + 3 + 2;
     static constexpr int kTmemSlot = kBars + kNumBars * 8;
     static constexpr int kTotal = kTmemSlot + 16;
     static_assert(kTotal <= 232448, "shared memory budget");
-    static_assert(kTileBytes % 1024 == 0, "swizzled tiles need 1024-byte alignment");
-    static constexpr int kColS = 0;
-    static constexpr int kColDP = 128;
+    static_assert(kTileBytes % 1024 == 0 && kSubTileBytes % 1024 == 0, "swizzled tiles need 1024-byte alignment");
+    // S^T / dP^T: two 32-column buffers each (sub-tile t uses buffer t & 1; released as soon as the compute warps have loaded
+    // them); P^T / dS^T: four packed 16-column buffers each (one per compute warpgroup; released by the dV / dK MMAs)
+    static constexpr int kColS = 0;        // + (t & 1) * 32
+    static constexpr int kColDP = 64;      // + (t & 1) * 32
+    static constexpr int kColP = 128;      // + j * 16
+    static constexpr int kColDS = 192;     // + j * 16
     static constexpr int kColDV = 256;
     static constexpr int kColDK = 256 + kD;
     static constexpr int kColDQ = 256 + 2 * kD;
@@ -92,44 +118,44 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
                  : "memory");
 }
 
-// P^T and dS^T for 32 query columns of one key row.
+// P^T and dS^T for 16 query columns of one key row (half a sub-tile).
 //   sr / dr : S^T, dP^T accumulators (fp32 bits), column c <-> query m0 + c
-//   nl / nd : shared-memory rows of -L * log2e and -delta for those 32 queries (broadcast 16-byte loads)
-//   bias    : kBiasMode 1: the 64 bytes of this row's transposed-bias chunk are at brow + ((chunk16 ^ (r & 7)) << 4)
-//             kBiasMode 3: band pointer such that bias(c) = bp[-c]  (or the constant bconst when kConst)
+//   nl / nd : shared-memory rows of -L * log2e and -delta for those 16 queries (broadcast 16-byte loads; the TMA producer
+//             copies them next to the Q / dO rows of the sub-tile)
+//   bias    : kBiasMode 1: bw[c / 2] holds the packed 16-bit bias values of columns c, c + 1
+//             kBiasMode 3: band pointer such that bias(c) = bp[-c]  (or the constant bconst, already times log2e, when kConst)
 //   vis_lo  : [kMask] columns c < vis_lo are masked (causal: query before the key; whole row when the key is out of range)
 template <bool kBf16, int kBiasMode, bool kMask, bool kConst, bool kSum>
-__device__ __forceinline__ void v3_chunk(const uint32_t (&sr)[32], const uint32_t (&dr)[32], const float* nl, const float* nd,
-                                         const uint8_t* brow, int chunk16_0, int rx, const float* bp, float bconst,
-                                         float scale_log2, int vis_lo, uint32_t (&pp)[16], uint32_t (&dd)[16], float& ds_sum) {
+__device__ __forceinline__ void v3_chunk(const uint32_t (&sr)[16], const uint32_t (&dr)[16], const float* nl, const float* nd,
+                                         const uint32_t* bw, const float* bp, float bconst, float scale_log2, int vis_lo,
+                                         uint32_t* pp, uint32_t* dd, float& ds_sum) {
     const f32x2 sc2 = f2_pack(scale_log2, scale_log2);
     const f32x2 l2e2 = f2_pack(kLog2e, kLog2e);
     f32x2 sum2 = f2_pack(0.f, 0.f);
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {                       // 8 columns per group
+    for (int g = 0; g < 2; ++g) {                       // 8 columns per group
         const float4 nla = *reinterpret_cast<const float4*>(nl + g * 8), nlb = *reinterpret_cast<const float4*>(nl + g * 8 + 4);
         const float4 nda = *reinterpret_cast<const float4*>(nd + g * 8), ndb = *reinterpret_cast<const float4*>(nd + g * 8 + 4);
         const float nlv[8] = {nla.x, nla.y, nla.z, nla.w, nlb.x, nlb.y, nlb.z, nlb.w};
         const float ndv[8] = {nda.x, nda.y, nda.z, nda.w, ndb.x, ndb.y, ndb.z, ndb.w};
-        uint32_t bw[4] = {0, 0, 0, 0};
-        if (kBiasMode == 1) {
-            const uint4 u = *reinterpret_cast<const uint4*>(brow + (((chunk16_0 + g) ^ rx) << 4));
-            bw[0] = u.x; bw[1] = u.y; bw[2] = u.z; bw[3] = u.w;
-        }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const int c = g * 8 + 2 * e;
             f32x2 t = f2_pack(nlv[2 * e], nlv[2 * e + 1]);
             if (kBiasMode == 1) {
-                const float2 bf = unpack2<kBf16>(bw[e]);
+                const float2 bf = unpack2<kBf16>(bw[c / 2]);
                 t = f2_fma(f2_pack(bf.x, bf.y), l2e2, t);
             } else if (kBiasMode == 3) {
-                if (kConst) t = f2_add(t, f2_pack(bconst, bconst));          // bconst already times log2e
+                if (kConst) t = f2_add(t, f2_pack(bconst, bconst));
                 else t = f2_fma(f2_pack(bp[-c], bp[-c - 1]), l2e2, t);
             }
             float a0, a1;
             f2_unpack(f2_fma(f2_pack_bits(sr[c], sr[c + 1]), sc2, t), a0, a1);
+#ifdef B200T5_DBG_SKIP_EXP
+            float p0 = a0 * 1e-3f, p1 = a1 * 1e-3f;
+#else
             float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
+#endif
             if (kMask) {
                 if (c < vis_lo) p0 = 0.f;
                 if (c + 1 < vis_lo) p1 = 0.f;
@@ -153,17 +179,21 @@ __device__ __forceinline__ void v3_chunk(const uint32_t (&sr)[32], const uint32_
 }  // namespace
 
 #ifdef B200T5_BWD_TIMING
-__device__ long long g_bwd3_ts[4][24][8];      // [role: wg0, wg1, mma, drain][iteration][slot]
+__device__ long long g_bwd3_ts[8][32][8];      // [role: wg0..wg3, mma B, drain, mma A, producer][iteration][slot]
 #define BWD3_TS(role, k, slot)                                                          \
     do {                                                                                \
-        if (blockIdx.x == 777 && (k) < 24) g_bwd3_ts[role][k][slot] = clock64();        \
+        if (blockIdx.x == 777 && (k) < 32) g_bwd3_ts[role][k][slot] = clock64();        \
     } while (0)
 #else
 #define BWD3_TS(role, k, slot) do { } while (0)
 #endif
 
+constexpr int kThreads = 896;        // 28 warps (warps are allocated four at a time: 25 would cost as much)
+constexpr int kWarpDrain0 = 16, kWarpTma = 20, kWarpMmaA = 21, kWarpMmaB = 22, kWarpC = 23, kWarpMmaA1 = 24, kWarpMmaB1 = 25, kWarpMmaA2 = 26,
+              kWarpMmaA3 = 27;
+
 template <int kD, bool kBf16, int kBiasMode, bool kCausal>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(kThreads, 1)     // 72 registers per thread at launch: a pool of 896 x 72 = 64 512 for setmaxnreg
 attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
     using C = Bwd3Cfg<kD>;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -187,48 +217,58 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
         i_start = first_row <= 0 ? 0 : first_row / kBM;
     }
     const int n_iter = p.num_m_blocks > i_start ? p.num_m_blocks - i_start : 0;
-    const int T = 2 * n_iter;
+    const int T = kNSub * n_iter;
 
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kBars);
     uint64_t* k_full = bars;
     uint64_t* kt_ready = bars + 1;
     uint64_t* qdo_full = bars + 2;
-    uint64_t* qdo_empty = qdo_full + C::kQStages;
-    uint64_t* b_full = qdo_empty + C::kQStages;
-    uint64_t* b_empty = b_full + C::kBiasStages;
-    uint64_t* sdp_full = b_empty + C::kBiasStages;      // [2] one per S^T / dP^T buffer
-    uint64_t* pds_full = sdp_full + 2;                  // [2]
-    uint64_t* dq_full = pds_full + 2;
+    uint64_t* qdo_empty = qdo_full + C::kSlots;
+    uint64_t* sdp_full = qdo_empty + C::kSlots;         // [4] S^T / dP^T of buffer j written          (MMA A -> compute j)
+    // [2][4] P^T / dS^T (and the dS^T box) of sub-tile j written, one set per tile parity (compute j -> MMA B, warp C).  An
+    // mbarrier probe only tells phases of opposite parity apart, so no waiter may fall two phases behind.  The B warps are tied
+    // to the warpgroups through pds_free, but warp C is not: a fast warpgroup signalled tiles 0 and 1 before C had looked at
+    // tile 0, and C waited for ever (found on B200 with the in-kernel bias, whose constant sub-tiles make the warpgroups
+    // uneven).  With one barrier set per tile parity a warpgroup would have to be two tiles ahead of C, which box_free forbids.
+    uint64_t* pds_full = sdp_full + kNSub;
+    uint64_t* pds_free = pds_full + 2 * kNSub;              // [4] dV, dK MMAs reading P^T / dS^T of j completed (MMA B -> compute j)
+    uint64_t* s_empty = pds_free + kNSub;               // [4] compute j has S^T of its sub-tile in registers  (compute j -> MMA A)
+    uint64_t* dp_empty = s_empty + kNSub;               // [4] ... and dP^T
+    uint64_t* dq_full = dp_empty + kNSub;
     uint64_t* dq_empty = dq_full + 1;
+    uint64_t* all_done = dq_empty + 1;                  // every MMA of the CTA completed (single phase: the epilogue's gate; B and C commit)
+    uint64_t* box_free = all_done + 1;                  // [2] dS^T boxes of tile parity: dQ MMAs done + TMA reduce reads done (C -> compute)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::kTmemSlot);
 
     if (threadIdx.x == 0) {
         if ((smem_u32(smem) & 1023u) != 0) __trap();
         mbar_init(k_full, 1);
         mbar_init(kt_ready, 4);
-        for (int i = 0; i < C::kQStages; ++i) {
+        for (int i = 0; i < C::kSlots; ++i) {
             mbar_init(qdo_full + i, 1);
             mbar_init(qdo_empty + i, 1);
         }
-        for (int i = 0; i < C::kBiasStages; ++i) {
-            mbar_init(b_full + i, 1);
-            mbar_init(b_empty + i, 4);
-        }
-        for (int i = 0; i < 2; ++i) {
+        mbar_init(all_done, 3);                           // the two B warps and warp C
+        mbar_init(box_free + 0, 2);
+        mbar_init(box_free + 1, 2);
+        for (int i = 0; i < kNSub; ++i) {
             mbar_init(sdp_full + i, 1);
-            mbar_init(pds_full + i, 1);
+            mbar_init(pds_full + i, 128);                 // every thread of compute warpgroup i arrives by itself
+            mbar_init(pds_full + kNSub + i, 128);
+            mbar_init(pds_free + i, 1);
+            mbar_init(s_empty + i, 4);
+            mbar_init(dp_empty + i, 4);
         }
         mbar_init(dq_full, 1);
         mbar_init(dq_empty, 4);
         fence_mbar_init();
     }
-    if (warp == 13) tmem_alloc<512>(tmem_slot);
-    if (warp == 12 && lane == 0) {
+    if (warp == kWarpMmaA) tmem_alloc<512>(tmem_slot);
+    if (warp == kWarpTma && lane == 0) {
         tma_prefetch_desc(&p.map_q);
         tma_prefetch_desc(&p.map_k);
         tma_prefetch_desc(&p.map_do);
         tma_prefetch_desc(&p.map_dq);
-        if (kBiasMode == 1) tma_prefetch_desc(&p.map_bias);
         if (kBiasMode != 0) tma_prefetch_desc(&p.map_ds);
     }
     tc_fence_before();
@@ -236,59 +276,57 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp >= 12) {
-        // =============================== control warps (12..15) ===============================
-        setmaxnreg_dec<40>();
-        if (warp == 12 && lane == 0 && n_iter > 0) {
-            // ---- K once; then the Q / dO ring (one stage = one 128-query tile) ----
+    if (warp >= kWarpTma) {
+        // =============================== control warps (20..27) ===============================
+        setmaxnreg_dec<32>();
+        constexpr uint32_t sbo = 8 * C::kRowBytes;
+        constexpr uint32_t hi_op = sdesc_hi(sbo, C::kSwizzle);       // Q, dO, K tiles (either major)
+        if (warp == kWarpTma && lane == 0 && n_iter > 0) {
+            // ---- K once; then the Q / dO ring (one slot = the 32 query rows of one sub-tile) ----
             mbar_arrive_expect_tx(k_full, C::kTileBytes);
             tma_load_4d(smem + C::kK, &p.map_k, k_full, 0, col0, h, b);
-            for (int k = 0; k < n_iter; ++k) {
-                const int s = k % C::kQStages;
-                const int mrow0 = (i_start + k) * kBM;
-                mbar_wait_producer(qdo_empty + s, ((k / C::kQStages) & 1) ^ 1);
-                mbar_arrive_expect_tx(qdo_full + s, 2 * C::kTileBytes);
-                tma_load_4d(smem + C::kQ + s * C::kTileBytes, &p.map_q, qdo_full + s, 0, mrow0, h, b);
-                tma_load_4d(smem + C::kDO + s * C::kTileBytes, &p.map_do, qdo_full + s, 0, mrow0, h, b);
-            }
-        } else if (warp == 14 && lane == 0 && kBiasMode == 1) {
-            // ---- transposed-bias tiles: box [64 queries][128 keys] per half tile ----
-            const int hb = p.bias_h_bcast ? 0 : h;
-            const int bb = p.bias_b_bcast ? 0 : b;
             for (int t = 0; t < T; ++t) {
-                const int s = t % C::kBiasStages;
-                const int m0 = (i_start + (t >> 1)) * kBM + (t & 1) * kSub;
-                mbar_wait_producer(b_empty + s, ((t / C::kBiasStages) & 1) ^ 1);
-                mbar_arrive_expect_tx(b_full + s, kBoxBytes);
-                tma_load_4d(smem + C::kBias + s * kBoxBytes, &p.map_bias, b_full + s, m0, col0, hb, bb);
+                const int s = t % C::kSlots;
+                const int m0 = (i_start + (t >> 2)) * kBM + (t & 3) * kSub;
+                BWD3_TS(7, t, 0);
+                mbar_wait_producer(qdo_empty + s, ((t / C::kSlots) & 1) ^ 1);
+                BWD3_TS(7, t, 1);
+                mbar_arrive_expect_tx(qdo_full + s, 2 * C::kSubTileBytes + 2 * kSub * 4);
+                tma_load_4d(smem + C::kQ + s * C::kSubTileBytes, &p.map_q, qdo_full + s, 0, m0, h, b);
+                tma_load_4d(smem + C::kDO + s * C::kSubTileBytes, &p.map_do, qdo_full + s, 0, m0, h, b);
+                // row statistics of the 32 queries (padded rows: always in range, 128-byte aligned)
+                float* st = reinterpret_cast<float*>(smem + C::kStats) + s * (2 * kSub);
+                const int64_t srow = ((int64_t)b * p.H + h) * p.m_pad + m0;
+                bulk_load_1d(st, p.nl + srow, kSub * 4, qdo_full + s);
+                bulk_load_1d(st + kSub, p.ndelta + srow, kSub * 4, qdo_full + s);
             }
-        } else if (warp == 13 && n_iter > 0) {
-            // ---- MMA issuer: the whole warp runs the loop (descriptor arithmetic stays warp-uniform), one elected
-            //      lane issues the tcgen05 instructions ----
+        } else if ((warp == kWarpMmaA || warp == kWarpMmaA1 || warp == kWarpMmaA2 || warp == kWarpMmaA3) && n_iter > 0) {
+            // ---- MMA warp A: S^T = K Q^T and dP^T = V dO^T of every sub-tile (A operands K, V in TMEM) ----
+            // (the whole warp runs the loop so that descriptor arithmetic stays warp-uniform; one elected lane issues)
             const bool leader = elect_one();
-            constexpr uint32_t idesc_s = make_idesc(kBf16, 128, kSub, false, false);   // S^T, dP^T : A tmem, B K-major
-            constexpr uint32_t idesc_dkv = make_idesc(kBf16, 128, kD, false, true);    // dV, dK     : A tmem, B MN-major
-            constexpr uint32_t idesc_dq = make_idesc(kBf16, 128, kD, true, true);      // dQ         : A, B MN-major
-            constexpr uint32_t sbo = 8 * C::kRowBytes;
-            constexpr uint32_t hi_op = sdesc_hi(sbo, C::kSwizzle);       // Q, dO, K tiles (either major)
-            constexpr uint32_t hi_ds = sdesc_hi(1024, kSwz128);          // dS^T boxes
+            constexpr uint32_t idesc_s = make_idesc(kBf16, 128, kSub, false, false);
             const uint32_t q_lo0 = sdesc_lo(smem_u32(smem + C::kQ), 16);
             const uint32_t do_lo0 = sdesc_lo(smem_u32(smem + C::kDO), 16);
-            const uint32_t q_mn_lo0 = sdesc_lo(smem_u32(smem + C::kQ), C::kTileBytes);
-            const uint32_t do_mn_lo0 = sdesc_lo(smem_u32(smem + C::kDO), C::kTileBytes);
-            const uint32_t k_mn_lo = sdesc_lo(smem_u32(smem + C::kK), C::kTileBytes);
-            const uint32_t ds_mn_lo = sdesc_lo(smem_u32(smem + C::kDS), kBoxBytes);     // A = dS (M = queries, 2 boxes)
             const uint32_t tm_kt = tmem_base + C::kColKt;
             const uint32_t tm_vt = tmem_base + C::kColVt;
-            const uint32_t tm_dv = tmem_base + C::kColDV;
-            const uint32_t tm_dk = tmem_base + C::kColDK;
-            const uint32_t tm_dq = tmem_base + C::kColDQ;
-
-            auto issue_s_dp = [&](int t) {
-                const int k = t >> 1, hh = t & 1;
-                const uint32_t so = (k % C::kQStages) * (C::kTileBytes >> 4) + hh * (C::kHalfTileBytes >> 4);
-                const uint32_t tm_s = tmem_base + C::kColS + hh * kSub;
-                const uint32_t tm_dp = tmem_base + C::kColDP + hh * kSub;
+            mbar_wait(kt_ready, 0);
+            const int j_mine = warp == kWarpMmaA ? 0 : (warp == kWarpMmaA1 ? 1 : (warp == kWarpMmaA2 ? 2 : 3));
+            for (int t = j_mine; t < T; t += kNSub) {
+                const int k = t >> 2, j = t & 3;
+                if (lane == 0) BWD3_TS(6, t, 0);
+                mbar_wait(qdo_full + (t % C::kSlots), (t / C::kSlots) & 1);
+                if (lane == 0) BWD3_TS(6, t, 1);
+                if (t >= 2) {
+                    // buffer t & 1 held sub-tile t - 2 (warpgroup (j + 2) & 3, tile (t - 2) >> 2): in registers by now?
+                    const int jp = (j + 2) & 3;
+                    const uint32_t par = ((t - 2) >> 2) & 1;
+                    mbar_wait(s_empty + jp, par);           // (S^T and dP^T are loaded together: one barrier)
+                }
+                tc_fence_after();
+                if (lane == 0) BWD3_TS(6, t, 2);
+                const uint32_t so = (t % C::kSlots) * (C::kSubTileBytes >> 4);
+                const uint32_t tm_s = tmem_base + C::kColS + (t & 1) * kSub;
+                const uint32_t tm_dp = tmem_base + C::kColDP + (t & 1) * kSub;
                 if (leader) {
 #pragma unroll
                     for (int kk = 0; kk < kD / 16; ++kk)
@@ -296,101 +334,135 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
 #pragma unroll
                     for (int kk = 0; kk < kD / 16; ++kk)
                         umma_ts2(tm_dp, tm_vt + kk * 8, do_lo0 + so + kk * 2, hi_op, idesc_s, kk > 0 ? 1u : 0u);
-                    umma_commit(sdp_full + hh);
+                    umma_commit(sdp_full + j);
                 }
                 __syncwarp();
-            };
-            auto issue_dv_dk = [&](int t) {
-                const int k = t >> 1, hh = t & 1;
-                const uint32_t so = (k % C::kQStages) * (C::kTileBytes >> 4) + hh * (C::kHalfTileBytes >> 4);
-                const uint32_t tm_p = tmem_base + C::kColS + hh * kSub;      // P^T  (packed 16-bit) over S^T
-                const uint32_t tm_ds = tmem_base + C::kColDP + hh * kSub;    // dS^T (packed 16-bit) over dP^T
+                if (lane == 0) BWD3_TS(6, t, 3);
+            }
+        } else if ((warp == kWarpMmaB || warp == kWarpMmaB1) && n_iter > 0) {
+            // ---- MMA warps B0 / B1: dV += P^T dO, dK += dS^T Q of the even / odd sub-tiles (A operands from TMEM).  The
+            //      accumulators were zero-filled by the drain warpgroup (kt_ready): the two warps' first MMAs come in any order ----
+            mbar_wait(kt_ready, 0);
+            const bool leader = elect_one();
+            constexpr uint32_t idesc_dkv = make_idesc(kBf16, 128, kD, false, true);    // A tmem, B MN-major
+            const uint32_t q_mn_lo0 = sdesc_lo(smem_u32(smem + C::kQ), C::kSubTileBytes);
+            const uint32_t do_mn_lo0 = sdesc_lo(smem_u32(smem + C::kDO), C::kSubTileBytes);
+            const uint32_t tm_dv = tmem_base + C::kColDV;
+            const uint32_t tm_dk = tmem_base + C::kColDK;
+            for (int t = (warp == kWarpMmaB ? 0 : 1); t < T; t += 2) {
+                const int k = t >> 2, j = t & 3;
+                if (lane == 0) BWD3_TS(4, t, 0);
+                mbar_wait(pds_full + (k & 1) * kNSub + j, (k >> 1) & 1);
+                tc_fence_after();
+                if (lane == 0) BWD3_TS(4, t, 1);
+                const uint32_t so = (t % C::kSlots) * (C::kSubTileBytes >> 4);
+                const uint32_t tm_p = tmem_base + C::kColP + j * 16;         // P^T  (packed 16-bit pairs)
+                const uint32_t tm_ds = tmem_base + C::kColDS + j * 16;       // dS^T (packed 16-bit pairs)
                 if (leader) {
-                    // dV += P^T dO ; dK += dS^T Q      (K dimension = the 64 queries of this half tile)
+                    // (K dimension = the 32 queries of this sub-tile)
 #pragma unroll
                     for (int kk = 0; kk < kSub / 16; ++kk)
-                        umma_ts2(tm_dv, tm_p + kk * 8, do_mn_lo0 + so + ((kk * 16 * C::kRowBytes) >> 4), hi_op, idesc_dkv,
-                                 (t > 0 || kk > 0) ? 1u : 0u);
+                        umma_ts2(tm_dv, tm_p + kk * 8, do_mn_lo0 + so + ((kk * 16 * C::kRowBytes) >> 4), hi_op, idesc_dkv, 1u);
 #pragma unroll
                     for (int kk = 0; kk < kSub / 16; ++kk)
-                        umma_ts2(tm_dk, tm_ds + kk * 8, q_mn_lo0 + so + ((kk * 16 * C::kRowBytes) >> 4), hi_op, idesc_dkv,
-                                 (t > 0 || kk > 0) ? 1u : 0u);
+                        umma_ts2(tm_dk, tm_ds + kk * 8, q_mn_lo0 + so + ((kk * 16 * C::kRowBytes) >> 4), hi_op, idesc_dkv, 1u);
+                    umma_commit(pds_free + j);
+                    // Q / dO slot: the S^T / dP^T MMAs of warp A that read it completed before the compute warps could produce
+                    // the P^T this warp just consumed, so this commit covers every reader of the slot
+                    umma_commit(qdo_empty + (t % C::kSlots));
+                    if (t >= T - 2) umma_commit(all_done);          // the last sub-tile of this warp (T is a multiple of 4)
                 }
                 __syncwarp();
-            };
-            auto issue_dq = [&](int k) {
+                if (lane == 0) BWD3_TS(4, t, 3);
+            }
+        } else if (warp == kWarpC && n_iter > 0) {
+            // ---- warp C: dS^T boxes -> dBias surface (TMA reduce-add / store), and dQ = dS K once per tile ----
+            const bool leader = elect_one();
+            constexpr uint32_t idesc_dq = make_idesc(kBf16, 128, kD, true, true);      // A, B MN-major
+            constexpr uint32_t hi_ds = sdesc_hi(8 * 64, kSwz64);                       // dS^T boxes: 64-byte rows
+            const uint32_t k_mn_lo = sdesc_lo(smem_u32(smem + C::kK), C::kTileBytes);
+            const uint32_t ds_mn_lo0 = sdesc_lo(smem_u32(smem + C::kDS), kBoxBytes);   // A = dS (M = queries, 4 boxes of 32)
+            const uint32_t tm_dq = tmem_base + C::kColDQ;
+            const int g_ds = b % p.ds_groups;
+            const bool rpe_skip = kBiasMode == 3 && p.rpe.dconst != nullptr;
+            for (int k = 0; k < n_iter; ++k) {
+                // second arrival for the boxes of the previous tile: its TMA group (committed a moment ago) has read them.  Done
+                // first thing, so that the boxes are free again one whole tile before their next use.
+                if (k > 0 && leader) {
+                    bulk_wait_group_read<0>();
+                    mbar_arrive(box_free + ((k - 1) & 1));
+                }
+                __syncwarp();
+                for (int j = 0; j < kNSub; ++j) {
+                    mbar_wait(pds_full + (k & 1) * kNSub + j, (k >> 1) & 1);
+                    if (kBiasMode != 0 && leader) {
+                        const int m0 = (i_start + k) * kBM + j * kSub;
+                        bool skip = false;
+                        if (kBiasMode == 3 && rpe_skip) {          // sub-tiles beyond a constant end of the table keep dS in the kernel
+                            const int rel_min = col0 - (m0 + kSub - 1), rel_max = col0 + (kBN - 1) - m0;
+                            skip = rel_max <= p.rpe.const_lo || rel_min >= p.rpe.const_hi;
+                        }
+#ifdef B200T5_DBG_SKIP_DS_TMA
+                        skip = true;
+#endif
+                        if (!skip) {
+                            const uint8_t* box = smem + C::kDS + ((k & 1) * kNSub + j) * kBoxBytes;
+                            if (p.ds_use_reduce) tma_reduce_add_4d(&p.map_ds, box, m0, col0, h, g_ds);
+                            else tma_store_4d(&p.map_ds, box, m0, col0, h, g_ds);
+                        }
+                    }
+                }
+                if (leader) bulk_commit_group();                    // one group per tile (possibly empty)
+                if (k == 0) mbar_wait(k_full, 0);
+                else mbar_wait(dq_empty, (k - 1) & 1);             // dQ(k-1) has been drained out of TMEM
+                tc_fence_after();
+                if (lane == 0) BWD3_TS(4, 4 * k + 3, 2);
+                const uint32_t ds_mn_lo = ds_mn_lo0 + (k & 1) * ((kNSub * kBoxBytes) >> 4);
                 if (leader) {
-                    // dQ_tile = dS K      (K dimension = the 128 keys of this CTA; A = dS^T boxes read MN-major)
+                    // dQ_tile = dS K   (K dimension = the 128 keys of this CTA; A = dS^T boxes read MN-major)
 #pragma unroll
                     for (int kk = 0; kk < kBN / 16; ++kk)
-                        umma_ss2(tm_dq, ds_mn_lo + kk * (2048 >> 4), hi_ds, k_mn_lo + ((kk * 16 * C::kRowBytes) >> 4), hi_op,
+                        umma_ss2(tm_dq, ds_mn_lo + kk * ((16 * 64) >> 4), hi_ds, k_mn_lo + ((kk * 16 * C::kRowBytes) >> 4), hi_op,
                                  idesc_dq, kk > 0 ? 1u : 0u);
                     umma_commit(dq_full);
-                    umma_commit(qdo_empty + (k % C::kQStages));
+                    umma_commit(box_free + (k & 1));                // first of the two arrivals: the MMAs have read the boxes
+                    if (k == n_iter - 1) umma_commit(all_done);
                 }
                 __syncwarp();
-            };
-
-            mbar_wait(kt_ready, 0);
-            mbar_wait(qdo_full + 0, 0);
-            tc_fence_after();
-            issue_s_dp(0);
-            for (int t = 0; t < T; ++t) {
-                const int k = t >> 1, hh = t & 1;
-                if (t + 1 < T) {
-                    const int tn = t + 1, kn = tn >> 1;
-                    if ((tn & 1) == 0) mbar_wait(qdo_full + (kn % C::kQStages), (kn / C::kQStages) & 1);
-                    // buffer (tn & 1) was last used by half tile t - 1: its P^T / dS^T were waited for (pds_full) and its
-                    // dV / dK MMAs issued in the previous iteration; MMAs execute in issue order
-                    tc_fence_after();
-                    issue_s_dp(tn);
-                }
-                if (lane == 0) BWD3_TS(2, t, 0);
-                mbar_wait(pds_full + hh, k & 1);
-                tc_fence_after();
-                if (lane == 0) BWD3_TS(2, t, 1);
-                issue_dv_dk(t);
-                if (hh == 1) {
-                    if (k == 0) mbar_wait(k_full, 0);
-                    else mbar_wait(dq_empty, (k - 1) & 1);    // dQ(k-1) has been drained out of TMEM
-                    tc_fence_after();
-                    if (lane == 0) BWD3_TS(2, t, 2);
-                    issue_dq(k);
-                }
-                if (lane == 0) BWD3_TS(2, t, 3);
             }
+            if (leader) bulk_wait_group<0>();                       // every store / reduction of this CTA has landed
         }
-    } else if (warp >= 8) {
-        // =============================== drain warpgroup (8..11) ===============================
-        setmaxnreg_dec<72>();
+    } else if (warp >= kWarpDrain0) {
+        // =============================== drain warpgroup (16..19) ===============================
+        setmaxnreg_dec<56>();
         const int r = (warp & 3) * 32 + lane;                 // TMEM lane
         const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
         if (n_iter > 0) {
             // ---- prologue: K and V rows of this key block -> TMEM (the A operands of S^T and dP^T) ----
             const int gn = col0 + r;
-            constexpr int kWords = kD / 2;
-            uint32_t kr[kWords], vr[kWords];
-            if (gn < p.N) {
-                const uint4* kp4 = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.k) +
-                                                                  2 * ((int64_t)b * p.k_sb + (int64_t)h * p.k_sh + (int64_t)gn * p.k_sn));
-                const uint4* vp4 = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.v) +
-                                                                  2 * ((int64_t)b * p.v_sb + (int64_t)h * p.v_sh + (int64_t)gn * p.v_sn));
 #pragma unroll
-                for (int i = 0; i < kWords / 4; ++i) {
-                    const uint4 a = __ldg(kp4 + i), c = __ldg(vp4 + i);
-                    kr[4 * i] = a.x; kr[4 * i + 1] = a.y; kr[4 * i + 2] = a.z; kr[4 * i + 3] = a.w;
-                    vr[4 * i] = c.x; vr[4 * i + 1] = c.y; vr[4 * i + 2] = c.z; vr[4 * i + 3] = c.w;
+            for (int which = 0; which < 2; ++which) {
+                const uint8_t* base = reinterpret_cast<const uint8_t*>(which == 0 ? p.k : p.v);
+                const int64_t off = which == 0 ? ((int64_t)b * p.k_sb + (int64_t)h * p.k_sh + (int64_t)gn * p.k_sn)
+                                               : ((int64_t)b * p.v_sb + (int64_t)h * p.v_sh + (int64_t)gn * p.v_sn);
+                const uint4* src = reinterpret_cast<const uint4*>(base + 2 * off);
+                const uint32_t tm_dst = tmem_base + lane_off + (which == 0 ? C::kColKt : C::kColVt);
+#pragma unroll
+                for (int i = 0; i < kD / 16; ++i) {                    // 8 words (16 elements) at a time
+                    uint4 a = make_uint4(0, 0, 0, 0), c = make_uint4(0, 0, 0, 0);
+                    if (gn < p.N) {
+                        a = __ldg(src + 2 * i);
+                        c = __ldg(src + 2 * i + 1);
+                    }
+                    const uint32_t w[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+                    tmem_st8(tm_dst + 8 * i, w);
                 }
-            } else {
-#pragma unroll
-                for (int i = 0; i < kWords; ++i) kr[i] = vr[i] = 0u;
             }
-            if constexpr (kWords == 8) {
-                tmem_st8(tmem_base + lane_off + C::kColKt, kr);
-                tmem_st8(tmem_base + lane_off + C::kColVt, vr);
-            } else {
-                tmem_st_n<kWords>(tmem_base + lane_off + C::kColKt, kr);
-                tmem_st_n<kWords>(tmem_base + lane_off + C::kColVt, vr);
+            {
+                // dV, dK accumulators start at zero (every dV / dK MMA accumulates: two warps issue them)
+                const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+                for (int c = 0; c < 2 * kD; c += 8) tmem_st8(tmem_base + lane_off + C::kColDV + c, z);
             }
             tmem_st_wait();
             tc_fence_before();
@@ -401,26 +473,25 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
         const int dq_c3 = (nb % p.dq_groups) * p.B + b;       // (group, batch) slice of the dQ surface
         uint8_t* stage_row = smem + C::kDQ + r * (kD * 2);
         for (int k = 0; k < n_iter; ++k) {
-            if (r == 0) BWD3_TS(3, k, 0);
+            if (r == 0) BWD3_TS(5, k, 0);
             mbar_wait(dq_full, k & 1);
             tc_fence_after();
-            if (r == 0) BWD3_TS(3, k, 1);
-            // (72 registers per thread here: convert chunk by chunk, keep only the packed words)
+            if (r == 0) BWD3_TS(5, k, 1);
+            // (56 registers per thread here: 16 columns at a time, keep only the packed words)
             uint32_t qp[kD / 2];
-            constexpr int kChunk = kD >= 32 ? 32 : 16;
 #pragma unroll
-            for (int c0 = 0; c0 < kD; c0 += kChunk) {
-                uint32_t q[kChunk];
-                tmem_ld_n<kChunk>(tm_dq + c0, q);
+            for (int c0 = 0; c0 < kD; c0 += 16) {
+                uint32_t q[16];
+                tmem_ld16(tm_dq + c0, q);
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < kChunk; i += 2) qp[(c0 + i) / 2] = pack2<kBf16>(__uint_as_float(q[i]), __uint_as_float(q[i + 1]));
+                for (int i = 0; i < 16; i += 2) qp[(c0 + i) / 2] = pack2<kBf16>(__uint_as_float(q[i]), __uint_as_float(q[i + 1]));
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(dq_empty);             // the dQ columns may be overwritten by tile k + 1
             if (r == 0) bulk_wait_group_read<0>();            // staging tile: the previous reduce has read it
-            named_bar_sync(3, 128);
+            named_bar_sync(5, 128);
 #pragma unroll
             for (int i = 0; i < kD; i += 8) {
                 const int c16 = i / 8;
@@ -428,76 +499,69 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
                 *reinterpret_cast<uint4*>(stage_row + off) = make_uint4(qp[i / 2], qp[i / 2 + 1], qp[i / 2 + 2], qp[i / 2 + 3]);
             }
             fence_proxy_async_smem();
-            named_bar_sync(3, 128);
+            named_bar_sync(5, 128);
             if (r == 0) {
+#ifndef B200T5_DBG_SKIP_DQ_TMA
                 tma_reduce_add_4d(&p.map_dq, smem + C::kDQ, 0, (i_start + k) * kBM, h, dq_c3);
+#endif
                 bulk_commit_group();
             }
-            if (r == 0) BWD3_TS(3, k, 2);
+            if (r == 0) BWD3_TS(5, k, 2);
         }
         if (r == 0) bulk_wait_group<0>();
     } else {
-        // =============================== compute warpgroups (0..3, 4..7) ===============================
-        setmaxnreg_inc<200>();
-        const int wg = warp >> 2;                             // half tile parity this warpgroup serves
+        // =============================== compute warpgroups 0..3 (warps 0..15) ===============================
+        setmaxnreg_inc<96>();     // the CTA owns 896 x 72 = 64 512 registers (its launch allocation): 512 x 96 + 128 x 56 (drain) + 256 x 32 (control)
+        const int wg = warp >> 2;                             // == j: the sub-tile of every tile / the buffer this warpgroup owns
         const int r = (warp & 3) * 32 + lane;                 // key row in the block == TMEM lane
         const int gn = col0 + r;                              // global key index
         const bool key_ok = gn < p.N;
         const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
-        const uint32_t tm_s = tmem_base + lane_off + C::kColS + wg * kSub;
-        const uint32_t tm_dp = tmem_base + lane_off + C::kColDP + wg * kSub;
-        uint8_t* const sDS = smem + C::kDS + wg * kBoxBytes + r * 128;
-        float* const stats = reinterpret_cast<float*>(smem + C::kStats) + wg * 256;     // [buf][2][64]
-        const int bar_id = 1 + wg;
-        const int rx = r & 7;
+        const uint32_t tm_s = tmem_base + lane_off + C::kColS + (wg & 1) * kSub;      // sub-tile t = 4k + wg uses buffer t & 1
+        const uint32_t tm_dp = tmem_base + lane_off + C::kColDP + (wg & 1) * kSub;
+        const uint32_t tm_p = tmem_base + lane_off + C::kColP + wg * 16;
+        const uint32_t tm_ds = tmem_base + lane_off + C::kColDS + wg * 16;
+        const int rx = (r >> 1) & 3;                          // 64-byte swizzle: 16-byte chunk ^= (row / 2) % 4
         const float scale_log2 = p.sm_scale * kLog2e;
-        const int64_t stat_base = ((int64_t)b * p.H + h) * p.M;
-        const int g_ds = b % p.ds_groups;
 
-        const float* band = reinterpret_cast<const float*>(smem + C::kBias);   // [bias mode 3]
+        const float* band = reinterpret_cast<const float*>(smem + C::kBand);   // [bias mode 3]
         if (kBiasMode == 3) {
-            float* dst = reinterpret_cast<float*>(smem + C::kBias);
+            float* dst = reinterpret_cast<float*>(smem + C::kBand);
             const float* src = p.rpe.band + (int64_t)h * p.rpe.band_len;
-            for (int i = threadIdx.x; i < p.rpe.band_len; i += 256) dst[i] = __ldg(src + i);
-            named_bar_sync(4, 256);
+            for (int i = threadIdx.x; i < p.rpe.band_len; i += 512) dst[i] = __ldg(src + i);
+            named_bar_sync(6, 512);
         }
         const bool rpe_skip = kBiasMode == 3 && p.rpe.dconst != nullptr;
         float ds_const_lo = 0.f, ds_const_hi = 0.f;
 
-        // row statistics of a half tile: thread i < 64 loads L, thread 64 + i loads delta of query m0 + i
-        auto load_stat = [&](int m0) -> float {
-            const int m = m0 + (r & 63);
-            float v = 0.f;
-            if (r < 64) {
-                v = -INFINITY;                                               // out-of-range query or L = -inf: P = 0
-                if (m < p.M) {
-                    const float Lv = __ldg(p.lse + stat_base + m);
-                    if (Lv != -INFINITY) v = -Lv * kLog2e;
-                }
-            } else if (m < p.M) {
-                v = -__ldg(p.delta + stat_base + m);
-            }
-            return v;
-        };
-        if (n_iter > 0) {
-            stats[r] = load_stat(i_start * kBM + wg * kSub);                 // buffer 0: [0,64) -L*log2e, [64,128) -delta
-            named_bar_sync(bar_id, 128);
+        // dense bias: repacked copy [bh][key block][32-query block][4][128 keys][8 queries] (16-bit)
+        const uint4* bias_blk = nullptr;
+        if (kBiasMode == 1) {
+            const int hb_n = p.bias_h_bcast ? 1 : p.H;
+            const int64_t bh = (int64_t)(p.bias_b_bcast ? 0 : b) * hb_n + (p.bias_h_bcast ? 0 : h);
+            const int64_t n_mb = kNSub * p.num_m_blocks;              // the copy covers whole 128-query tiles
+            bias_blk = reinterpret_cast<const uint4*>(p.bias) + ((bh * nnb + nb) * n_mb) * (4 * 128) + r;
         }
+        // The 64 bytes of bias this thread needs for its next sub-tile are copied global -> shared with cp.async (no registers:
+        // they would be live across a whole sub-tile) into the band's shared memory (mode 3 is the other user): [wg][chunk][row].
+        uint4* const bias_stage = reinterpret_cast<uint4*>(smem + C::kBand) + wg * (4 * 128) + r;
+        auto load_bias = [&](int m0) {
+            const uint4* src = bias_blk + (int64_t)(m0 / kSub) * (4 * 128);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) cp_async_16(bias_stage + c * 128, src + c * 128);
+        };
+        if (n_iter > 0 && kBiasMode == 1) load_bias(i_start * kBM + wg * kSub);
 
         for (int k = 0; k < n_iter; ++k) {
-            const int mrow0 = (i_start + k) * kBM;
-            const int m0 = mrow0 + wg * kSub;
-            const int t = 2 * k + wg;
-            const float* st = stats + (k & 1) * 128;
-            float stat_next = 0.f;
-            if (k + 1 < n_iter) stat_next = load_stat(m0 + kBM);
+            const int m0 = (i_start + k) * kBM + wg * kSub;
+            uint8_t* const sDS = smem + C::kDS + ((k & 1) * kNSub + wg) * kBoxBytes + r * 64;
 
             // masks: key tail (whole row) and causal (query m sees key n iff n <= m + pseq, i.e. c >= gn - pseq - m0)
             const bool need_mask = (col0 + kBN > p.N) || (kCausal && (col0 + kBN - 1 - pseq > m0));
             int vis_lo = 0;
             if (kCausal) vis_lo = gn - pseq - m0;
             if (!key_ok) vis_lo = kSub;
-            // bias mode 3: relative positions n - m of this half tile
+            // bias mode 3: relative positions n - m of this sub-tile
             bool rpe_const = false;
             float rpe_cval = 0.f;
             bool const_is_lo = false;
@@ -509,143 +573,126 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
                 if (rpe_const) rpe_cval = band[(const_is_lo ? p.rpe.const_lo : p.rpe.const_hi) - p.rpe.band_lo] * kLog2e;
             }
 
-            // ---------------- P^T and dS^T of this half tile, in registers ----------------
             if (r == 0) BWD3_TS(wg, k, 0);
             mbar_wait(sdp_full + wg, k & 1);
             tc_fence_after();
             if (r == 0) BWD3_TS(wg, k, 1);
-            const int bstage = t % C::kBiasStages;
-            if (kBiasMode == 1) mbar_wait(b_full + bstage, (t / C::kBiasStages) & 1);
-            const uint8_t* brow = smem + C::kBias + bstage * kBoxBytes + r * 128;
-            uint32_t pp[2][16], dd[2][16];
+
+            // ---------------- S^T (whole sub-tile) and dP^T (half by half) into registers; the buffers go back to warp A at
+            //                  once.  P^T, dS^T of each half of 16 queries go to this warpgroup's own TMEM columns (A operands
+            //                  of dV, dK) and to the shared-memory box (dQ, dBias) ----------------
+            uint32_t sr[32], drr[32];
+            tmem_ld32(tm_s, sr);
+            tmem_ld32(tm_dp, drr);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_empty + wg);
+            if (kBiasMode == 1) cp_async_wait_all();               // this thread's own copies: nobody else reads them
 #pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
-                uint32_t sr[32], dr[32];
-                tmem_ld32(tm_s + ch * 32, sr);
-                tmem_ld32(tm_dp + ch * 32, dr);
-                tmem_ld_wait();
-                const float* nl = st + ch * 32;
-                const float* nd = st + 64 + ch * 32;
-                // bias mode 3, element c of the chunk: band[(gn - (m0 + ch*32 + c)) - band_lo]
-                const float* bp = band + (gn - m0 - ch * 32 - p.rpe.band_lo);
-                const int vl = vis_lo - ch * 32;
+            for (int hc = 0; hc < 2; ++hc) {
+                uint32_t pp[8], dd[8], bias_h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                if (kBiasMode == 1) {
+                    const uint4 u0 = bias_stage[(2 * hc) * 128], u1 = bias_stage[(2 * hc + 1) * 128];
+                    bias_h[0] = u0.x; bias_h[1] = u0.y; bias_h[2] = u0.z; bias_h[3] = u0.w;
+                    bias_h[4] = u1.x; bias_h[5] = u1.y; bias_h[6] = u1.z; bias_h[7] = u1.w;
+                }
+                const uint32_t(&dr)[16] = *reinterpret_cast<const uint32_t(*)[16]>(drr + hc * 16);
+                // statistics of the slot: the S^T MMAs of this sub-tile were issued after warp A saw the slot's barrier complete
+                const float* nl = reinterpret_cast<const float*>(smem + C::kStats) + ((4 * k + wg) % C::kSlots) * (2 * kSub) + hc * 16;
+                const float* nd = nl + kSub;
+                // bias mode 3, element c of this half: band[(gn - (m0 + 16 hc + c)) - band_lo]
+                const float* bp = band + (gn - m0 - hc * 16 - p.rpe.band_lo);
+                const int vl = vis_lo - hc * 16;
+                const uint32_t* bw = bias_h;
+                const uint32_t(&srh)[16] = *reinterpret_cast<const uint32_t(*)[16]>(sr + hc * 16);
                 if (kBiasMode == 3 && rpe_const) {
                     float* acc = const_is_lo ? &ds_const_lo : &ds_const_hi;
                     if (rpe_skip) {
-                        if (need_mask) v3_chunk<kBf16, 3, true, true, true>(sr, dr, nl, nd, nullptr, 0, rx, bp, rpe_cval, scale_log2, vl, pp[ch], dd[ch], *acc);
-                        else v3_chunk<kBf16, 3, false, true, true>(sr, dr, nl, nd, nullptr, 0, rx, bp, rpe_cval, scale_log2, 0, pp[ch], dd[ch], *acc);
+                        if (need_mask) v3_chunk<kBf16, 3, true, true, true>(srh, dr, nl, nd, bw, bp, rpe_cval, scale_log2, vl, pp, dd, *acc);
+                        else v3_chunk<kBf16, 3, false, true, true>(srh, dr, nl, nd, bw, bp, rpe_cval, scale_log2, 0, pp, dd, *acc);
                     } else {
-                        if (need_mask) v3_chunk<kBf16, 3, true, true, false>(sr, dr, nl, nd, nullptr, 0, rx, bp, rpe_cval, scale_log2, vl, pp[ch], dd[ch], *acc);
-                        else v3_chunk<kBf16, 3, false, true, false>(sr, dr, nl, nd, nullptr, 0, rx, bp, rpe_cval, scale_log2, 0, pp[ch], dd[ch], *acc);
+                        if (need_mask) v3_chunk<kBf16, 3, true, true, false>(srh, dr, nl, nd, bw, bp, rpe_cval, scale_log2, vl, pp, dd, *acc);
+                        else v3_chunk<kBf16, 3, false, true, false>(srh, dr, nl, nd, bw, bp, rpe_cval, scale_log2, 0, pp, dd, *acc);
                     }
                 } else {
                     float dummy = 0.f;
-                    if (need_mask) v3_chunk<kBf16, kBiasMode, true, false, false>(sr, dr, nl, nd, brow, ch * 4, rx, bp, 0.f, scale_log2, vl, pp[ch], dd[ch], dummy);
-                    else v3_chunk<kBf16, kBiasMode, false, false, false>(sr, dr, nl, nd, brow, ch * 4, rx, bp, 0.f, scale_log2, 0, pp[ch], dd[ch], dummy);
+                    if (need_mask) v3_chunk<kBf16, kBiasMode, true, false, false>(srh, dr, nl, nd, bw, bp, 0.f, scale_log2, vl, pp, dd, dummy);
+                    else v3_chunk<kBf16, kBiasMode, false, false, false>(srh, dr, nl, nd, bw, bp, 0.f, scale_log2, 0, pp, dd, dummy);
                 }
-            }
-            if (kBiasMode == 1) {
-                fence_proxy_async_smem();                    // bias reads complete before TMA refills the stage
-                __syncwarp();
-                if (lane == 0) mbar_arrive(b_empty + bstage);
+                if (hc == 0 && k > 0) {
+                    mbar_wait(pds_free + wg, (k - 1) & 1);        // dV,dK of this warpgroup's previous sub-tile have read P^T / dS^T
+                    // the dS^T box (tile parity, j) was last used two tiles ago: its dQ MMAs and its TMA reduce have read it
+                    if (k >= 2) mbar_wait(box_free + (k & 1), ((k >> 1) - 1) & 1);
+                    tc_fence_after();
+                }
+                tmem_st8(tm_p + hc * 8, pp);
+                tmem_st8(tm_ds + hc * 8, dd);
+                *reinterpret_cast<uint4*>(sDS + (((2 * hc) ^ rx) << 4)) = make_uint4(dd[0], dd[1], dd[2], dd[3]);
+                *reinterpret_cast<uint4*>(sDS + (((2 * hc + 1) ^ rx) << 4)) = make_uint4(dd[4], dd[5], dd[6], dd[7]);
             }
             if (r == 0) BWD3_TS(wg, k, 2);
-
-            // ---------------- the dS^T box of this warpgroup is free again ----------------
-            // (last readers: the dQ MMAs of tile k - 1 and the TMA reduce of this warpgroup's previous box)
-            if (k > 0) mbar_wait(dq_full, (k - 1) & 1);
-            if (r == 0) bulk_wait_group_read<0>();
-            named_bar_sync(bar_id, 128);
-            if (r == 0) BWD3_TS(wg, k, 3);
-
-            // ---------------- P^T, dS^T -> TMEM (A operands of dV, dK); dS^T -> shared memory (dQ, dBias) ----------------
-            tmem_st16(tm_s + 0, pp[0]);
-            tmem_st16(tm_s + 16, pp[1]);
-            tmem_st16(tm_dp + 0, dd[0]);
-            tmem_st16(tm_dp + 16, dd[1]);
-#pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
-#pragma unroll
-                for (int c8 = 0; c8 < 4; ++c8) {
-                    const int off = ((ch * 4 + c8) ^ rx) << 4;
-                    *reinterpret_cast<uint4*>(sDS + off) =
-                        make_uint4(dd[ch][c8 * 4], dd[ch][c8 * 4 + 1], dd[ch][c8 * 4 + 2], dd[ch][c8 * 4 + 3]);
-                }
-            }
-            if (k + 1 < n_iter) stats[((k + 1) & 1) * 128 + r] = stat_next;
+            if (kBiasMode == 1 && k + 1 < n_iter) load_bias(m0 + kBM);     // lands during the wait for the next S^T
             tmem_st_wait();
             tc_fence_before();
             fence_proxy_async_smem();
-            named_bar_sync(bar_id, 128);
-            if (r == 0) BWD3_TS(wg, k, 4);
-            if (r == 0) {
-                mbar_arrive(pds_full + wg);
-                if (kBiasMode != 0 && !(kBiasMode == 3 && rpe_skip && rpe_const)) {
-                    if (p.ds_use_reduce) tma_reduce_add_4d(&p.map_ds, smem + C::kDS + wg * kBoxBytes, m0, col0, h, g_ds);
-                    else tma_store_4d(&p.map_ds, smem + C::kDS + wg * kBoxBytes, m0, col0, h, g_ds);
-                    bulk_commit_group();
-                }
-            }
+            mbar_arrive(pds_full + (k & 1) * kNSub + wg);
+            if (r == 0) BWD3_TS(wg, k, 3);
         }
 
-        // ---- tail: dV (warpgroup 0) and dK * sm_scale (warpgroup 1) once every MMA of the CTA has completed ----
+        // ---- tail: constant-tile sums; then dV (warpgroups 0, 1: D/2 columns each) and dK * sm_scale (warpgroups 2, 3) ----
         if (kBiasMode == 3 && rpe_skip) {
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
                 ds_const_lo += __shfl_xor_sync(0xffffffffu, ds_const_lo, off);
                 ds_const_hi += __shfl_xor_sync(0xffffffffu, ds_const_hi, off);
             }
-            // (the stats buffers are free: every thread of the warpgroup passed the last barrier of the loop)
-            float* red = stats;
-            named_bar_sync(bar_id, 128);
             if (lane == 0) {
-                red[(warp & 3) * 2 + 0] = ds_const_lo;
-                red[(warp & 3) * 2 + 1] = ds_const_hi;
-            }
-            named_bar_sync(bar_id, 128);
-            if (r < 2) {
-                const float tsum = red[r] + red[2 + r] + red[4 + r] + red[6 + r];
-                if (tsum != 0.f) atomicAdd(p.rpe.dconst + h * 2 + r, tsum);
+                if (ds_const_lo != 0.f) atomicAdd(p.rpe.dconst + h * 2 + 0, ds_const_lo);
+                if (ds_const_hi != 0.f) atomicAdd(p.rpe.dconst + h * 2 + 1, ds_const_hi);
             }
         }
         {
-            uint8_t* out_row = wg == 0
+            const bool is_dv = wg < 2;
+            constexpr int kColsPer = kD / 2;                          // columns of the accumulator this warpgroup writes
+            const int c_first = (wg & 1) * kColsPer;
+            uint8_t* out_row = is_dv
                 ? reinterpret_cast<uint8_t*>(p.dv) + 2 * ((int64_t)b * p.dv_sb + (int64_t)h * p.dv_sh + (int64_t)gn * p.dv_sn)
                 : reinterpret_cast<uint8_t*>(p.dk) + 2 * ((int64_t)b * p.dk_sb + (int64_t)h * p.dk_sh + (int64_t)gn * p.dk_sn);
-            const float sc = wg == 0 ? 1.f : p.sm_scale;
+            const float sc = is_dv ? 1.f : p.sm_scale;
             if (n_iter > 0) {
-                mbar_wait(dq_full, (n_iter - 1) & 1);            // every MMA of this CTA has completed
+                // every MMA of warp B -- the last writers of dV / dK -- completed.  (A dedicated single-phase barrier: the compute
+                // warps no longer follow dq_full tile by tile, so its parity alone could match a phase two tiles old.)
+                mbar_wait(all_done, 0);
                 tc_fence_after();
-                const uint32_t tm_acc = tmem_base + lane_off + (wg == 0 ? C::kColDV : C::kColDK);
-                constexpr int kChunk = kD >= 32 ? 32 : 16;
+                const uint32_t tm_acc = tmem_base + lane_off + (is_dv ? C::kColDV : C::kColDK) + c_first;
 #pragma unroll
-                for (int c0 = 0; c0 < kD; c0 += kChunk) {
-                    uint32_t a[kChunk];
-                    tmem_ld_n<kChunk>(tm_acc + c0, a);
+                for (int c0 = 0; c0 < kColsPer; c0 += 8) {
+                    uint32_t a[8];
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                 : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7])
+                                 : "r"(tm_acc + c0)
+                                 : "memory");
                     tmem_ld_wait();
                     if (key_ok) {
-#pragma unroll
-                        for (int i = 0; i < kChunk; i += 8) {
-                            uint4 out;
-                            out.x = pack2<kBf16>(__uint_as_float(a[i + 0]) * sc, __uint_as_float(a[i + 1]) * sc);
-                            out.y = pack2<kBf16>(__uint_as_float(a[i + 2]) * sc, __uint_as_float(a[i + 3]) * sc);
-                            out.z = pack2<kBf16>(__uint_as_float(a[i + 4]) * sc, __uint_as_float(a[i + 5]) * sc);
-                            out.w = pack2<kBf16>(__uint_as_float(a[i + 6]) * sc, __uint_as_float(a[i + 7]) * sc);
-                            *reinterpret_cast<uint4*>(out_row + 2 * (c0 + i)) = out;
-                        }
+                        uint4 out;
+                        out.x = pack2<kBf16>(__uint_as_float(a[0]) * sc, __uint_as_float(a[1]) * sc);
+                        out.y = pack2<kBf16>(__uint_as_float(a[2]) * sc, __uint_as_float(a[3]) * sc);
+                        out.z = pack2<kBf16>(__uint_as_float(a[4]) * sc, __uint_as_float(a[5]) * sc);
+                        out.w = pack2<kBf16>(__uint_as_float(a[6]) * sc, __uint_as_float(a[7]) * sc);
+                        *reinterpret_cast<uint4*>(out_row + 2 * (c_first + c0)) = out;
                     }
                 }
                 tc_fence_before();
             } else if (key_ok) {
 #pragma unroll
-                for (int c = 0; c < kD; c += 8) *reinterpret_cast<uint4*>(out_row + 2 * c) = make_uint4(0, 0, 0, 0);
+                for (int c = 0; c < kColsPer; c += 8) *reinterpret_cast<uint4*>(out_row + 2 * (c_first + c)) = make_uint4(0, 0, 0, 0);
             }
         }
-        if (r == 0) bulk_wait_group<0>();     // all TMA stores / reductions of this warpgroup have landed
     }
 
     __syncthreads();
-    if (warp == 13) {
+    if (warp == kWarpMmaA) {
         tc_fence_after();
         tmem_dealloc<512>(tmem_base);
     }
@@ -661,21 +708,22 @@ static cudaError_t launch_bwd3_inst(const AttnBwdKernelParams& kp, cudaStream_t 
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal);
     if (e != cudaSuccess) return e;
     const int grid = kp.B * kp.H * kp.num_n_blocks;
-    kern<<<grid, 512, C::kTotal, stream>>>(kp);
+    kern<<<grid, kThreads, C::kTotal, stream>>>(kp);
     count_launch();
 #ifdef B200T5_BWD_TIMING
     {
         cudaDeviceSynchronize();
-        static long long ts[4][24][8];
+        static long long ts[8][32][8];
         cudaMemcpyFromSymbol(ts, g_bwd3_ts, sizeof(ts));
         const long long t0 = ts[0][0][0];
-        const char* names[4] = {"wg0 [wait S, S ready, math done, box free, stored]", "wg1", "mma [wait P/dS(t), P/dS ready, dq gate, issued]  (per half tile)",
-                                "drain [wait dQ, dQ ready, reduce issued]"};
-        for (int role = 0; role < 4; ++role) {
+        const char* names[8] = {"wg0 [wait S, S ready, math done, stored + signalled]  (per tile)", "wg1", "wg2", "wg3",
+                                "mma B [wait P/dS(t), ready, dq gate (warp C), issued]  (per sub-tile)", "drain [wait dQ, dQ ready, reduce issued]  (per tile)",
+                                "mma A [wait Q/dO slot, slot ready, buffers free, issued]  (per sub-tile)", "producer [wait slot empty, empty]  (per sub-tile)"};
+        for (int role = 0; role < 8; ++role) {
             printf("BWD3_TIMING %s\n", names[role]);
-            for (int k = 0; k < (role == 2 ? 16 : 8); ++k) {
+            for (int k = 0; k < ((role == 4 || role >= 6) ? 32 : 8); ++k) {
                 printf("  %2d:", k);
-                for (int j = 0; j < 5; ++j) printf(" %7lld", ts[role][k][j] ? ts[role][k][j] - t0 : 0);
+                for (int j = 0; j < 4; ++j) printf(" %7lld", ts[role][k][j] ? ts[role][k][j] - t0 : 0);
                 printf("\n");
             }
         }

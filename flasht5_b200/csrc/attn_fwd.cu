@@ -36,16 +36,6 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kRescaleThreshold = 8.0f * kLn2;   // keep a stale max while exp(x - m) <= 256
 
-// Developer switch (A/B builds, tools/build_variant.sh): of every 8 column pairs, this many take their exp2 through the
-// FMA-pipe polynomial instead of the MUFU.  0 = product build.
-#ifndef B200T5_EXP2_POLY
-#define B200T5_EXP2_POLY 0
-#endif
-// Developer switch: with sm_scale == 1 the dense bias is added with the mixed-precision add (common.cuh: add_f32_16x2).
-#ifndef B200T5_BIAS_FHADD
-#define B200T5_BIAS_FHADD 0
-#endif
-
 template <int kD>
 struct FwdSmem {
     static constexpr int kRowBytes = (kD >= 64 ? 64 : kD) * 2;   // bytes per smem row inside one swizzle box
@@ -314,7 +304,8 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdKernelParams p) {
         const uint32_t tm_p = tmem_base + lane_off + L::kPCol;
 
         float m_ref = -INFINITY;   // running reference max (natural units, scaled + biased scores)
-        float l_sum = 0.f;
+        float l_sum = 0.f;         // sum of exp(x - m_ref), unrounded: L = m_ref + ln(l_sum)
+        float l_hat = 0.f;         // sum of the same values after rounding to the io dtype: normalises O
 
         const float* band = reinterpret_cast<const float*>(smem + L::kBias);   // [bias mode 3]
         if (kBiasMode == 3) {
@@ -359,21 +350,6 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdKernelParams p) {
                     const int s = it % kBiasStages;
                     mbar_wait(bars.b_full + s, (it / kBiasStages) & 1);
                     const uint8_t* brow = smem + L::kBias + s * kBiasHalfBytes + r * 128;
-#if B200T5_BIAS_FHADD
-                    if (p.sm_scale == 1.f) {
-                        // developer build: bias add straight from the packed 16-bit pair (one FHADD per element)
-#pragma unroll
-                        for (int c8 = 0; c8 < 8; ++c8) {
-                            const uint4 u = *reinterpret_cast<const uint4*>(brow + ((c8 ^ (r & 7)) << 4));
-                            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const int c = hh * 64 + c8 * 8 + e * 2;
-                                add_f32_16x2<kBf16>(w[e], x[c], x[c + 1], x[c], x[c + 1]);
-                            }
-                        }
-                    } else
-#endif
 #pragma unroll
                     for (int c8 = 0; c8 < 8; ++c8) {
                         const uint4 u = *reinterpret_cast<const uint4*>(brow + ((c8 ^ (r & 7)) << 4));
@@ -450,27 +426,37 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdKernelParams p) {
                 alpha = __expf(m_ref - tmax);              // exp(-inf) = 0 on the first tile
                 m_ref = tmax;
             }
-            const float m_safe = (m_ref == -INFINITY) ? 0.f : m_ref;
+            // Rows whose running max is the dtype's most negative value (the reference model folds padding masks into the bias
+            // as finfo.min, modeling_flash_t5.py:266-270): m * log2e would overflow, so such rows subtract first, as the
+            // reference does (exp2((s - m) * log2e), flash_attention_v2_bias.py:453-454).  Never taken for ordinary rows.
+            const bool huge_m = m_ref < -1e37f && m_ref != -INFINITY;
+            if (__any_sync(0xffffffffu, huge_m)) {
+                const float sub = huge_m ? m_ref : 0.f;
+#pragma unroll
+                for (int c = 0; c < kBN; ++c) x[c] -= sub;
+            }
+            const float m_safe = (m_ref == -INFINITY || huge_m) ? 0.f : m_ref;
             const float neg_m_log2 = -m_safe * kLog2e;
             FWD_TS(0, j, 4);
 
+            // P = exp2(.) rounded to the io dtype feeds the P V contraction; O is normalised by the sum of the ROUNDED values
+            // (l_hat), so the rounding of a dominant P cancels in the ratio, while L = m + ln(sum of the unrounded values)
+            // stays exact for the backward.  (Measured against the reference Triton kernel, profiles/r2a_triton_parity_*:
+            // with the stale reference max of the lazy rescale a dominant P is no longer exactly 1, and normalising by the
+            // exact sum left O at 1.96e-3 relative error where Triton has 1.66e-3.)
             uint32_t pk[kBN / 2];
-            float s0 = 0.f, s1 = 0.f;
+            float s0 = 0.f, s1 = 0.f, r0 = 0.f, r1 = 0.f;
 #pragma unroll
             for (int c = 0; c < kBN; c += 2) {
-                float e0, e1;
-                if (B200T5_EXP2_POLY > 0 && ((c / 2) % 8) < B200T5_EXP2_POLY) {
-                    // developer switch: this pair takes the FMA-pipe exp2 (common.cuh) instead of the MUFU
-                    ex2_poly_pair(fmaf(x[c], kLog2e, neg_m_log2), fmaf(x[c + 1], kLog2e, neg_m_log2), e0, e1);
-                } else {
-                    e0 = ex2_approx(fmaf(x[c], kLog2e, neg_m_log2));
-                    e1 = ex2_approx(fmaf(x[c + 1], kLog2e, neg_m_log2));
-                }
+                const float e0 = ex2_approx(fmaf(x[c], kLog2e, neg_m_log2));
+                const float e1 = ex2_approx(fmaf(x[c + 1], kLog2e, neg_m_log2));
                 s0 += e0;
                 s1 += e1;
                 pk[c / 2] = pack2<kBf16>(e0, e1);
+                add_f32_16x2<kBf16>(pk[c / 2], r0, r1, r0, r1);
             }
             l_sum = l_sum * alpha + (s0 + s1);
+            l_hat = l_hat * alpha + (r0 + r1);
             FWD_TS(0, j, 5);
 
             if (j > 0) {
@@ -514,12 +500,7 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdKernelParams p) {
         if (num_tiles > 0) {
             mbar_wait(bars.pv_done, (num_tiles - 1) & 1);
             tc_fence_after();
-#if B200T5_EXP2_POLY > 0
-            // the polynomial clamps exp2(-inf) to 2^-125 instead of 0: a row with no visible key is recognised by its max
-            const float inv_l = (l_sum > 0.f && m_ref != -INFINITY) ? 1.f / l_sum : 0.f;
-#else
-            const float inv_l = l_sum > 0.f ? 1.f / l_sum : 0.f;
-#endif
+            const float inv_l = l_hat > 0.f ? 1.f / l_hat : 0.f;
             constexpr int kChunk = kD >= 32 ? 32 : 16;
 #pragma unroll
             for (int c0 = 0; c0 < kD; c0 += kChunk) {
@@ -568,30 +549,6 @@ static cudaError_t launch_fwd_inst(const AttnFwdKernelParams& kp, cudaStream_t s
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     if (e != cudaSuccess) return e;
     const int grid = kp.B * kp.H * kp.num_m_blocks;
-    // two CTAs per SM need the full shared-memory carveout; ask for it instead of leaving it to the driver's heuristic
-    static const int carveout = getenv("B200T5_DEBUG_FWD_CARVEOUT") ? atoi(getenv("B200T5_DEBUG_FWD_CARVEOUT")) : -2;
-    if (carveout >= -1) {
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
-        if (e != cudaSuccess) return e;
-    }
-#ifdef B200T5_FWD_TIMING
-    {
-        int nb = -1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 256, L::kTotal);
-        cudaFuncAttributes fa;
-        cudaFuncGetAttributes(&fa, kern);
-        printf("FWD_TIMING occupancy API: %d CTAs/SM; regs %d, static smem %zu, dynamic %d, carveout pref %d (env %d)\n", nb,
-               fa.numRegs, fa.sharedSizeBytes, (int)L::kTotal, fa.preferredShmemCarveout, carveout);
-    }
-#endif
-    static const int extra_smem = getenv("B200T5_DEBUG_EXTRA_SMEM") ? atoi(getenv("B200T5_DEBUG_EXTRA_SMEM")) : 0;
-    if (extra_smem > 0) {
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal + extra_smem);
-        if (e != cudaSuccess) return e;
-        kern<<<grid, 256, L::kTotal + extra_smem, stream>>>(kp);
-        count_launch();
-        return cudaGetLastError();
-    }
 #ifdef B200T5_FWD_TIMING
     {
         int zero = 0;

@@ -188,14 +188,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(addr, parity)) return;
     uint32_t spins = 0;
     uint64_t t0 = 0;
-    while (!mbar_try_wait(addr, parity)) {
+    while (!mbar_try_wait(addr, parity & 1u)) {
         if (B200T5_WATCHDOG_NS != 0 && (++spins & 0x3FFu) == 0) {
             const uint64_t now = globaltimer_ns();
             if (t0 == 0) t0 = now;
             else if (now - t0 > B200T5_WATCHDOG_NS) {
 #ifdef B200T5_DEBUG_DEADLOCK
-                printf("b200t5: mbarrier deadlock block(%d,%d,%d) thread %d bar@%u parity %u\n", blockIdx.x, blockIdx.y,
-                       blockIdx.z, threadIdx.x, addr, parity);
+                // developer build: every stuck waiter reports (once), the kernel is killed a few periods later
+                static __device__ int reports;
+                if (parity < 2) printf("b200t5: mbarrier deadlock block(%d,%d,%d) thread %d bar@%u parity %u\n", blockIdx.x, blockIdx.y,
+                                       blockIdx.z, threadIdx.x, addr, parity);
+                parity |= 2u;                                   // (bit 1 is ignored by try_wait's predicate below)
+                if (now - t0 > 4 * B200T5_WATCHDOG_NS || atomicAdd(&reports, 1) > 4000) __trap();
+                continue;
 #endif
                 __trap();
             }
@@ -245,6 +250,20 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
         : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
           "r"(c2), "r"(c3)
         : "memory");
+}
+
+// 16 bytes global -> shared without passing through registers (LDGSTS); completion through cp.async.wait_all of the same thread
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// contiguous bytes global -> shared (multiple of 16, both 16-byte aligned), completion counted on an mbarrier like a tensor load
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :
+                 : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
 }
 
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2,

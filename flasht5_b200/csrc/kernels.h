@@ -48,9 +48,9 @@ struct AttnBwdKernelParams {
     CUtensorMap map_v;      // (D, N, H, B)
     CUtensorMap map_do;     // (D, M, H, B)
     CUtensorMap map_bias;   // (N, M, Hb, Bb)                                 [bias mode 1]
-                            // v3 kernel (D <= 64): the TRANSPOSED copy (M, N, Hb, Bb), box (64 queries, 128 keys)
+                            // (the v3 kernel, D <= 64, reads a repacked copy through `bias` instead)
     CUtensorMap map_ds;     // (N, M, H, B) 16-bit dS workspace, row pitch = N rounded up to 8   [bias modes 1, 2]
-                            // v3 kernel (D <= 64): the TRANSPOSED surface (M, N, H, G), row pitch = M rounded up to 8
+                            // v3 kernel (D <= 64): the TRANSPOSED surface (M, N, H, G), row pitch = M rounded up to 8, box (32, 128)
     const void* k;          // raw K / V pointers + element strides: the v3 kernel copies its key block into TMEM itself
     int64_t k_sb, k_sh, k_sn;
     const void* v;
@@ -62,8 +62,11 @@ struct AttnBwdKernelParams {
     int64_t dk_sb, dk_sh, dk_sn;
     void* dv;
     int64_t dv_sb, dv_sh, dv_sn;
-    const float* lse;       // (B, H, M)
-    const float* delta;     // (B, H, M)
+    const float* lse;       // (B, H, M)        [D = 128 kernel]
+    const float* delta;     // (B, H, M)        [D = 128 kernel]
+    const float* nl;        // (B, H, m_pad) -L * log2e (-inf: P = 0)   [v3 kernel: statistics as the kernel consumes them]
+    const float* ndelta;    // (B, H, m_pad) -delta
+    int m_pad;              // M rounded up to 128
     int B, H, M, N;
     int num_m_blocks, num_n_blocks;
     int bias_b_bcast, bias_h_bcast;
@@ -85,13 +88,28 @@ cudaError_t launch_attn_bwd(const AttnBwdKernelParams& kp, int D, bool bf16, int
 // transposed-formulation kernel (attn_bwd_v3.cu), D <= 64, bias modes 0, 1 (through the transposed copy), 3
 cudaError_t launch_attn_bwd_v3(const AttnBwdKernelParams& kp, int D, bool bf16, int bias_mode, bool causal,
                                cudaStream_t stream);
-// biasT[bb, hb, n, m] = bias[bb, hb, m, n] (16-bit elements, arbitrary input strides, output row pitch m_pitch)
-cudaError_t launch_bias_transpose(const void* bias, const int64_t* strides, void* bias_t, int Bb, int Hb, int M, int N,
-                                  int m_pitch, cudaStream_t stream);
+// Repacked copy of a dense bias for the v3 kernel: out[bh][key block of 128][query block of 32][c = 0..3][n = 0..127][8]
+// = bias[bh][32 * qb + 8 * c + e][128 * kb + n] (16-bit elements, arbitrary input strides, zero beyond M / N)
+cudaError_t launch_bias_repack(const void* bias, const int64_t* strides, void* bias_p, int Bb, int Hb, int M, int N,
+                               cudaStream_t stream);
+// v3 kernel helpers fused pairwise (independent work in one launch, block-index split):
+//   pre : delta + zero-fills (+ the bias repack when bias != NULL)        post : dQ conversion (+ transposing dBias reduce when dbias != NULL)
+//   (the row statistics are written in the form the v3 kernel consumes: nl = -L * log2e and ndelta = -delta, rows padded to m_pad)
+cudaError_t launch_attn_bwd_pre_fused(const void* o, const int64_t* o_strides, const void* dout, const int64_t* do_strides,
+                                      const float* lse, float* nl_out, float* ndelta_out, int m_pad, void* dq_ws, int dq_groups,
+                                      int B, int H, int M, int N, int D, bool bf16, void* zero_ptr, size_t zero_bytes,
+                                      const void* bias, const int64_t* bias_strides, void* bias_p, int Bb, int Hb,
+                                      cudaStream_t stream);
+cudaError_t launch_attn_bwd_post_fused(const void* dq_ws, int dq_groups, void* dq, const int64_t* dq_strides, int B, int H, int M,
+                                       int N, int D, float sm_scale, bool bf16, const void* ds_t, int m_pitch, void* dbias,
+                                       const int64_t* dbias_strides, int G, int reduce_b, int reduce_h, bool causal, bool out_f32,
+                                       cudaStream_t stream);
 // dbias[bb,hb,m,n] = sum over broadcast batch-group / head of ds_t[g,h,n,m] (the transposed surface of the v3 kernel);
 // fp32 accumulation, one rounding; causal-masked entries are written as 0 without being read
+// out_f32: dbias is an fp32 tensor (unrounded sums) instead of the io dtype
 cudaError_t launch_dbias_reduce_t(const void* ds_t, int m_pitch, void* dbias, const int64_t* dbias_strides, int G, int H,
-                                  int M, int N, int reduce_b, int reduce_h, bool causal, bool bf16, cudaStream_t stream);
+                                  int M, int N, int reduce_b, int reduce_h, bool causal, bool bf16, bool out_f32,
+                                  cudaStream_t stream);
 
 // delta[b,h,m] = sum_d O*dO  (fp32); also zero-fills the 16-bit dQ group surface (dq_groups, B, H, M, D).
 // `zero_ptr` / `zero_bytes` (multiple of 16, may be 0): an extra surface to zero-fill in the same launch.

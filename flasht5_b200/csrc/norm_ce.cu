@@ -261,120 +261,6 @@ __global__ void __launch_bounds__(256, 2) rmsnorm_bwd_vec_kernel(const void* __r
     for (int c = threadIdx.x; c < n; c += blockDim.x) dw_partial[(int64_t)blockIdx.x * n + c] = sdw[c];
 }
 
-// Backward, vectorised, two rows in flight per warp (developer variant, B200T5_RMSNORM_BWD_PREFETCH=1; 16-bit
-// activations, n <= 1024).  rmsnorm_bwd_vec_kernel measured 0.34-0.45 of the HBM roof: a warp loads a row, reduces, stores
-// and only then touches the next row, so with 16 warps per SM too few bytes are in flight.  Here the raw 16-byte vectors
-// of the NEXT row are requested before the current row is reduced, and the current row is kept packed (x and dy are
-// unpacked twice, which costs ALU slots this kernel has to spare) so that the extra registers fit two blocks per SM.
-template <int kXDt, int kWDt, int kChunks>
-__global__ void __launch_bounds__(256, 2) rmsnorm_bwd_vec2_kernel(const void* __restrict__ dy, const void* __restrict__ x,
-                                                                  const void* __restrict__ w, const float* __restrict__ rstd_in,
-                                                                  void* __restrict__ dx, float* __restrict__ dw_partial,
-                                                                  int rows, int n, int64_t dys, int64_t xs, int64_t dxs) {
-    static_assert(kXDt != 2, "16-bit activations only");
-    extern __shared__ float sdyn[];   // [n] dW block partial, then [n] fp32 copy of w
-    float* sdw = sdyn;
-    float* sw = sdyn + n;
-    constexpr int kGroups = 8;        // one warp per row
-    const int tig = threadIdx.x & 31;
-    const int group_global = blockIdx.x * kGroups + (threadIdx.x >> 5);
-    const int groups_total = gridDim.x * kGroups;
-    for (int c = threadIdx.x; c < n; c += blockDim.x) {
-        sdw[c] = 0.f;
-        sw[c] = load1<kWDt>(w, c);
-    }
-    __syncthreads();
-
-    float dwv[kChunks][8];
-#pragma unroll
-    for (int c = 0; c < kChunks; ++c)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) dwv[c][e] = 0.f;
-    const float inv_n = 1.f / static_cast<float>(n);
-    const uint16_t* xb = static_cast<const uint16_t*>(x);
-    const uint16_t* dyb = static_cast<const uint16_t*>(dy);
-
-    uint4 xr[kChunks], dr[kChunks], xn[kChunks], dn[kChunks];
-    float rstd_next = 0.f;
-    auto fetch = [&](int row, uint4 (&xo)[kChunks], uint4 (&dout)[kChunks], float& rs) {
-        rs = __ldg(rstd_in + row);
-#pragma unroll
-        for (int c = 0; c < kChunks; ++c) {
-            const int col = (c * 32 + tig) * 8;
-            if (col < n) {
-                xo[c] = __ldg(reinterpret_cast<const uint4*>(xb + (int64_t)row * xs + col));
-                dout[c] = __ldg(reinterpret_cast<const uint4*>(dyb + (int64_t)row * dys + col));
-            }
-        }
-    };
-    auto unpack8 = [](const uint4& u, float (&v)[8]) {
-        const uint32_t wd[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float2 f = unpack2<kXDt == 1>(wd[e]);
-            v[2 * e] = f.x;
-            v[2 * e + 1] = f.y;
-        }
-    };
-
-    int row = group_global;
-    if (row < rows) fetch(row, xn, dn, rstd_next);
-    for (; row < rows; row += groups_total) {
-        const float rstd = rstd_next;
-#pragma unroll
-        for (int c = 0; c < kChunks; ++c) {
-            xr[c] = xn[c];
-            dr[c] = dn[c];
-        }
-        if (row + groups_total < rows) fetch(row + groups_total, xn, dn, rstd_next);      // next row on its way
-        float c1 = 0.f;
-#pragma unroll
-        for (int c = 0; c < kChunks; ++c) {
-            const int col = (c * 32 + tig) * 8;
-            if (col < n) {
-                float xv[8], dv[8];
-                unpack8(xr[c], xv);
-                unpack8(dr[c], dv);
-                const float4 w0 = *reinterpret_cast<const float4*>(sw + col);
-                const float4 w1 = *reinterpret_cast<const float4*>(sw + col + 4);
-                const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const float xh = xv[e] * rstd;
-                    c1 = fmaf(xh, wv[e] * dv[e], c1);
-                    dwv[c][e] = fmaf(dv[e], xh, dwv[c][e]);
-                }
-            }
-        }
-        c1 = warp_sum(c1) * inv_n;
-#pragma unroll
-        for (int c = 0; c < kChunks; ++c) {
-            const int col = (c * 32 + tig) * 8;
-            if (col < n) {
-                float xv[8], dv[8], o[8];
-                unpack8(xr[c], xv);
-                unpack8(dr[c], dv);
-                const float4 w0 = *reinterpret_cast<const float4*>(sw + col);
-                const float4 w1 = *reinterpret_cast<const float4*>(sw + col + 4);
-                const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = (wv[e] * dv[e] - (xv[e] * rstd) * c1) * rstd;
-                store8<kXDt>(dx, (int64_t)row * dxs + col, o);
-            }
-        }
-    }
-#pragma unroll
-    for (int c = 0; c < kChunks; ++c) {
-        const int col = (c * 32 + tig) * 8;
-        if (col < n) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) atomicAdd(&sdw[col + e], dwv[c][e]);
-        }
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < n; c += blockDim.x) dw_partial[(int64_t)blockIdx.x * n + c] = sdw[c];
-}
-
 template <int kXDt, int kWDt>
 __global__ void __launch_bounds__(256) rmsnorm_bwd_generic_kernel(const void* __restrict__ dy, const void* __restrict__ x,
                                                                   const void* __restrict__ w, const float* __restrict__ rstd_in,
@@ -434,7 +320,8 @@ __global__ void __launch_bounds__(kCeThreads) ce_fwd_kernel(const void* __restri
             float loss = 0.f, z = 0.f;
             if (label != ignore_index) {
                 z = lse_square_scale * lse * lse;
-                loss = lse - load1<kDt>(logits, base + label) + z;
+                // a label outside [0, vocab) contributes no cross-entropy term (reference cross_entropy_loss.py:87-100)
+                loss = (label >= 0 && label < vocab ? lse - load1<kDt>(logits, base + label) : 0.f) + z;
             }
             losses[row] = loss;
             z_losses[row] = z;
@@ -491,11 +378,16 @@ __global__ void __launch_bounds__(kCeThreads) ce_fwd_kernel(const void* __restri
         const int64_t label = labels[row];
         float loss = 0.f, z = 0.f;
         if (label != ignore_index) {
-            const float xl = load1<kDt>(logits, base + label) * logit_scale;
-            if (smoothing > 0.f)
-                loss = lse - smoothing * (btot * logit_scale) / static_cast<float>(vocab) - (1.f - smoothing) * xl;
-            else
-                loss = lse - xl;
+            if (label >= 0 && label < vocab) {
+                const float xl = load1<kDt>(logits, base + label) * logit_scale;
+                if (smoothing > 0.f)
+                    loss = lse - smoothing * (btot * logit_scale) / static_cast<float>(vocab) - (1.f - smoothing) * xl;
+                else
+                    loss = lse - xl;
+            } else {
+                // label out of range: no cross-entropy term, only the smoothing term (reference cross_entropy_loss.py:96-100)
+                loss = smoothing > 0.f ? smoothing * (lse - (btot * logit_scale) / static_cast<float>(vocab)) : 0.f;
+            }
             z = lse_square_scale * lse * lse;
             loss += z;
         }
@@ -635,22 +527,7 @@ cudaError_t launch_rmsnorm_bwd(const void* dy, const void* x, const void* w, con
                                        (dys * xb) % 16 == 0 && (dxs * xb) % 16 == 0);
     int blocks = 0;
     if (rows > 0) {
-        const char* pf = getenv("B200T5_RMSNORM_BWD_PREFETCH");      // developer variant: two rows in flight per warp
-        if (pl.vec && pl.threads_per_row == 32 && x_dtype != 2 && pf && atoi(pf) != 0) {
-            blocks = std::min((rows + 7) / 8, kRmsnormMaxPartials);
-            const size_t smem = 2 * (size_t)n * sizeof(float);
-#define B200T5_RMS_BWD2(CH)                                                                                      \
-    B200T5_DISPATCH_DT(w_dtype, WD, {                                                                            \
-        if (x_dtype == 1) rmsnorm_bwd_vec2_kernel<1, WD, CH><<<blocks, 256, smem, stream>>>(dy, x, w, rstd, dx, dw_partial, rows, n, dys, xs, dxs); \
-        else rmsnorm_bwd_vec2_kernel<0, WD, CH><<<blocks, 256, smem, stream>>>(dy, x, w, rstd, dx, dw_partial, rows, n, dys, xs, dxs); })
-            switch (pl.chunks) {
-                case 1: B200T5_RMS_BWD2(1); break;
-                case 2: B200T5_RMS_BWD2(2); break;
-                case 3: B200T5_RMS_BWD2(3); break;
-                default: B200T5_RMS_BWD2(4); break;
-            }
-#undef B200T5_RMS_BWD2
-        } else if (pl.vec) {
+        if (pl.vec) {
             const int groups = 256 / pl.threads_per_row;
             blocks = std::min((rows + groups - 1) / groups, kRmsnormMaxPartials);
             const size_t smem = 2 * (size_t)n * sizeof(float);

@@ -12,7 +12,7 @@ from typing import Optional, Tuple
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_batch", "allreduce_dbias", "allreduce_dbias_overlapped", "allreduce_dtable"]
+__all__ = ["shard_batch", "allreduce_dbias", "allreduce_dbias_overlapped", "allreduce_dbias_f32", "allreduce_dtable", "comm_group"]
 
 
 def shard_batch(global_batch: int, rank: int, world_size: int) -> Tuple[int, int]:
@@ -57,3 +57,44 @@ def allreduce_dtable(dtable: Optional[torch.Tensor], group=None) -> Optional[tor
     the (num_buckets, H) table gradient -- 1 KB instead of the 33.5 MB dBias of the dense operator at the headline
     shape -- summed over ranks in fp32.  (Inside a DDP-wrapped model this is simply the embedding weight's bucket.)"""
     return allreduce_dbias(dtable, group)
+
+
+def comm_group(max_ctas: int = 8):
+    """A process group for the dBias exchange whose NCCL kernels are capped at `max_ctas` CTAs.  The exchange runs on a side
+    stream BESIDE attention kernels that fill every SM (2 048-CTA grids); NCCL's default of up to 32 CTAs per collective took
+    SMs and ~100 MB of HBM traffic from them (round 1: the backward kernel slowed from 0.306 to 0.341 ms at 2-8 ranks).  The
+    message is 33.5 MB per step: a handful of CTAs moves it well within one step.  Falls back to the default group when
+    the backend is not NCCL or the option is unavailable."""
+    if not dist.is_available() or not dist.is_initialized():
+        return None
+    try:
+        if dist.get_backend() != "nccl":
+            return None
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.config.max_ctas = int(max_ctas)
+        opts.config.min_ctas = 1
+        return dist.new_group(ranks=list(range(dist.get_world_size())), backend="nccl", pg_options=opts)
+    except Exception:      # noqa: BLE001  (older torch / NCCL without per-communicator config)
+        return None
+
+
+def allreduce_dbias_f32(dbias_f32: Optional[torch.Tensor], out_dtype: torch.dtype, comm_stream: "Optional[torch.cuda.Stream]" = None,
+                        group=None) -> Optional[torch.Tensor]:
+    """Exchange for the UNROUNDED fp32 dBias of `torch.ops.b200t5.attn_bias_bwd_f32dbias`: all-reduce it in place across the
+    data-parallel group and round ONCE to `out_dtype` -- no widening cast before and no second rounding after the
+    collective.  With `comm_stream` the collective and the cast are enqueued there (overlapping what the caller launches
+    next); the result is valid once the consumer has waited on that stream."""
+    if dbias_f32 is None:
+        return None
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    if comm_stream is None or not dbias_f32.is_cuda:
+        if multi:
+            dist.all_reduce(dbias_f32, op=dist.ReduceOp.SUM, group=group)
+        return dbias_f32.to(out_dtype)
+    comm_stream.wait_stream(torch.cuda.current_stream(dbias_f32.device))
+    with torch.cuda.stream(comm_stream):
+        if multi:
+            dist.all_reduce(dbias_f32, op=dist.ReduceOp.SUM, group=group)
+        out = dbias_f32.to(out_dtype)
+    dbias_f32.record_stream(comm_stream)
+    return out

@@ -17,7 +17,12 @@ Triton, no eager and no CPU fallback: without the built library or an sm_100 GPU
 
 Differences from the reference, all deliberate:
   * dBias is summed over EVERY broadcast dim of bias (the reference only sums the batch dim and
-    races on a broadcast head dim), accumulated in fp32 and rounded once.
+    races on a broadcast head dim).  Up to 8 batch elements meet in one 16-bit TMA reduce-add
+    group at L2; the groups (and a broadcast head dim) are then summed in fp32 and rounded once.
+  * q/k/v/o whose strides are not multiples of 8 elements (or are 0: expanded views) are
+    materialised with .contiguous() first -- TMA needs 16-byte aligned, non-degenerate strides --
+    so `o` is then contiguous instead of sharing q's strides.  An expanded bias takes the
+    strided pointer path in the forward and the repacked copy in the backward.
   * with bias=None the backward op returns an empty tensor in the `ds` slot (a custom op cannot
     return None); the autograd.Function turns it back into None.
 """
@@ -31,14 +36,16 @@ import torch
 
 from . import _cabi
 
-__all__ = ["flash_attention_v2_bias", "FlashAttentionAdditiveBias", "attn_bias_fwd", "attn_bias_bwd"]
+__all__ = ["flash_attention_v2_bias", "FlashAttentionAdditiveBias", "attn_bias_fwd", "attn_bias_bwd", "attn_bias_bwd_f32dbias"]
 
 
 def _aligned(t: torch.Tensor) -> bool:
     """What the C ABI needs (TMA): unit last stride, 16-byte base, other strides multiples of 8."""
     if t.stride(-1) != 1 or t.data_ptr() % 16 != 0:
         return False
-    return all(s % 8 == 0 for s, n in zip(t.stride()[:-1], t.shape[:-1]) if n > 1)
+    # (stride 0 on a dimension > 1 -- an expanded view such as k.expand(...) for multi-query attention -- cannot be put in a
+    #  TMA tensor map: such tensors are materialised by _prep; the reference Triton kernel honours them through its strides)
+    return all(s % 8 == 0 and s > 0 for s, n in zip(t.stride()[:-1], t.shape[:-1]) if n > 1)
 
 
 def _prep(t: torch.Tensor) -> torch.Tensor:
@@ -75,6 +82,8 @@ def _base_params(q, k, v, bias, causal, sm_scale) -> _cabi.AttnParams:
     p.sm_scale = float(sm_scale)
     p.device = q.device.index if q.device.index is not None else torch.cuda.current_device()
     p.stream = _cabi.stream_ptr(q.device)
+    # torch.use_deterministic_algorithms(True): fixed-order dQ / dBias accumulation in the backward (larger workspace)
+    p.flags = _cabi.ATTN_DETERMINISTIC if torch.are_deterministic_algorithms_enabled() else 0
     p.q, p.q_strides = q.data_ptr(), _cabi.strides4(q)
     p.k, p.k_strides = k.data_ptr(), _cabi.strides4(k)
     p.v, p.v_strides = v.data_ptr(), _cabi.strides4(v)
@@ -139,6 +148,40 @@ def attn_bias_bwd(o: torch.Tensor, do: torch.Tensor, q: torch.Tensor, k: torch.T
     p.workspace, p.workspace_bytes = ws.data_ptr(), nbytes
     _cabi.check(lib.b200t5_attn_bwd(C.byref(p)), "b200t5_attn_bwd")
     return dq, dk, dv, ds
+
+
+@torch.library.custom_op("b200t5::attn_bias_bwd_f32dbias", mutates_args=(), device_types="cuda")
+def attn_bias_bwd_f32dbias(o: torch.Tensor, do: torch.Tensor, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor,
+                           bias: torch.Tensor, L: torch.Tensor, causal: bool,
+                           sm_scale: float) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """As attn_bias_bwd, but dBias comes back as an UNROUNDED fp32 tensor (C ABI flag B200T5_ATTN_DBIAS_F32; head dims
+    16 / 32 / 64): the data-parallel exchange sums it across ranks and rounds once (data_parallel.allreduce_dbias_f32)."""
+    _cabi.require_cuda(o, do, q, k, v, bias, L)
+    B, H, M, N, D = _check_shapes(q, k, v, bias)
+    lib = _cabi.load()
+    q, k, v, o, do = _prep(q), _prep(k), _prep(v), _prep(o), _prep(do)
+    L = L.contiguous()
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    ds = torch.empty(bias.shape, dtype=torch.float32, device=q.device)
+    p = _base_params(q, k, v, bias, causal, sm_scale)
+    p.flags |= _cabi.ATTN_DBIAS_F32
+    p.o, p.o_strides = o.data_ptr(), _cabi.strides4(o)
+    p.lse = L.data_ptr()
+    p.dout, p.do_strides = do.data_ptr(), _cabi.strides4(do)
+    p.dq, p.dq_strides = dq.data_ptr(), _cabi.strides4(dq)
+    p.dk, p.dk_strides = dk.data_ptr(), _cabi.strides4(dk)
+    p.dv, p.dv_strides = dv.data_ptr(), _cabi.strides4(dv)
+    p.dbias, p.dbias_strides = ds.data_ptr(), _cabi.strides4(ds)
+    nbytes = lib.b200t5_attn_bwd_workspace_bytes(C.byref(p))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=q.device)
+    p.workspace, p.workspace_bytes = ws.data_ptr(), nbytes
+    _cabi.check(lib.b200t5_attn_bwd(C.byref(p)), "b200t5_attn_bwd")
+    return dq, dk, dv, ds
+
+
+@torch.library.register_fake("b200t5::attn_bias_bwd_f32dbias")
+def _attn_bias_bwd_f32dbias_fake(o, do, q, k, v, bias, L, causal, sm_scale):
+    return torch.empty_like(q), torch.empty_like(k), torch.empty_like(v), torch.empty(bias.shape, dtype=torch.float32, device=q.device)
 
 
 @torch.library.register_fake("b200t5::attn_bias_bwd")

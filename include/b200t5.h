@@ -56,6 +56,16 @@ enum { B200T5_F16 = 0, B200T5_BF16 = 1, B200T5_F32 = 2 };
  * mask (visible iff n <= m + N - M), lse = ln sum exp S (natural log), rows with no visible key
  * give o = 0 and lse = -inf.
  * ---------------------------------------------------------------------------------------------- */
+/* flags of b200t5_attn_params: with B200T5_ATTN_DETERMINISTIC the backward gives every key block its own slice of the dQ
+ * surface and every batch element its own slice of the dS surface, so that no two partial results ever meet in an
+ * L2 reduce-add and the final sums run in a fixed order: dQ and dBias are then bitwise reproducible run to run (dK, dV, O, L
+ * always are), at the price of a larger workspace (the workspace query honours the flag). */
+#define B200T5_ATTN_DETERMINISTIC 1
+/* B200T5_ATTN_DBIAS_F32 (backward, head dims 16 / 32 / 64): `dbias` points at an fp32 tensor of bias's shape (strides in fp32
+ * elements); the sum over the broadcast dimensions is delivered unrounded, so that a data-parallel caller can all-reduce it
+ * across ranks and round ONCE afterwards (flasht5_b200/data_parallel.py). */
+#define B200T5_ATTN_DBIAS_F32 2
+
 typedef struct b200t5_attn_params {
     /* problem */
     int32_t B, H, M, N, D;
@@ -65,7 +75,7 @@ typedef struct b200t5_attn_params {
     int32_t bias_H;       /* 1 or H */
     float sm_scale;
     int32_t device;       /* CUDA device ordinal the pointers live on */
-    int32_t reserved0;
+    int32_t flags;        /* 0, or B200T5_ATTN_DETERMINISTIC (backward only; was reserved0 = 0 in ABI version 1 callers) */
     void* stream;         /* cudaStream_t */
 
     /* forward operands */

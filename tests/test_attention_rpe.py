@@ -352,10 +352,12 @@ def test_cuda_fused_equals_dense_operator(shape):
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape", [(2, 4, 512, 512, 64, False), (2, 2, 640, 384, 16, True)], ids=lambda s: "x".join(map(str, s)))
 def test_cuda_constant_tile_skip(shape):
-    """B200T5_RPE_SKIP_CONST=1 (developer switch, off by default): tiles entirely beyond a constant end of the bucket
-    table keep their dS in the kernel instead of storing it.  dQ/dK/dV must not change; the table gradient is compared
-    with the fp64 oracle on the scale of the |dS| mass that flows into each bucket (the second shape is the degenerate
-    one: every visible position falls into ONE bucket, whose exact gradient is 0 because rows of dS sum to zero)."""
+    """Backward of the fused operator (compile-time level 2, csrc/api.cu): sub-tiles entirely beyond a constant end of the
+    bucket table keep their dS in the kernel (two fp32 sums per CTA), the other tiles reduce into the transposed surface and
+    the table gradient is folded straight from it.  dQ/dK/dV must equal the composed dense route (to the order of the 16-bit
+    partial sums for dQ); the table gradient is compared with the fp64 oracle on the scale of the |dS| mass that flows into
+    each bucket (the second shape is the degenerate one: every visible position falls into ONE bucket, whose exact gradient
+    is 0 because rows of dS sum to zero)."""
     from flasht5_b200 import flash_attention_v2_rpe
     B, H, M, N, D, causal = shape
     g = torch.Generator().manual_seed(11)
@@ -363,36 +365,26 @@ def test_cuda_constant_tile_skip(shape):
     q, k, v, do = mk(M), mk(N), mk(N), mk(M)
     w = 0.5 * torch.randn(H, 32, generator=g)
     outs = {}
-    old = os.environ.get("B200T5_RPE_SKIP_CONST")
-    # level 2 (table gradient straight from the non-constant tiles of the surface) has not run on hardware yet
-    levels = ("0", "1", "2") if os.environ.get("B200T5_RPE_SKIP2_GPU") == "1" else ("0", "1")
-    try:
-        for skip in levels:
-            os.environ["B200T5_RPE_SKIP_CONST"] = skip
-            qq, kk, vv, ww = (t.to(DEV).requires_grad_(True) for t in (q, k, v, w))
-            o = flash_attention_v2_rpe(qq, kk, vv, ww, 128, causal=causal, sm_scale=1.0, fused=True)
-            outs[skip] = (o,) + torch.autograd.grad(o, (qq, kk, vv, ww), do.to(DEV))
-            torch.cuda.synchronize()
-    finally:
-        if old is None:
-            os.environ.pop("B200T5_RPE_SKIP_CONST", None)
+    levels = ("dense", "fused")
+    for route in levels:
+        qq, kk, vv, ww = (t.to(DEV).requires_grad_(True) for t in (q, k, v, w))
+        o = flash_attention_v2_rpe(qq, kk, vv, ww, 128, causal=causal, sm_scale=1.0, fused=(route == "fused"))
+        outs[route] = (o,) + torch.autograd.grad(o, (qq, kk, vv, ww), do.to(DEV))
+        torch.cuda.synchronize()
+    for i, name in enumerate(("o", "dq", "dk", "dv")):
+        a, b = outs["dense"][i], outs["fused"][i]
+        if name == "dq":                                  # order of 16-bit partial sums at L2 differs run to run (~2.5e-3)
+            assert orc.error_metrics(b, a.double())[1] < 6e-3
         else:
-            os.environ["B200T5_RPE_SKIP_CONST"] = old
-    for skip in levels[1:]:
-        for i, name in enumerate(("o", "dq", "dk", "dv")):
-            a, b = outs["0"][i], outs[skip][i]
-            if name == "dq":                                  # order of 16-bit partial sums at L2 differs run to run (~2.5e-3)
-                assert orc.error_metrics(b, a.double())[1] < 6e-3
-            else:
-                assert torch.equal(a, b), name
+            assert torch.equal(a, b), name
     table = w.t().contiguous()
     bias = orc.t5_bias(table, M, N, bidirectional=not causal).to(torch.bfloat16).float()
     ref = orc.attn_fwd_bwd(q.float(), k.float(), v.float(), bias, do.float(), causal, 1.0)
     dt_ref = orc.t5_dtable(ref[5], M, N, not causal)
     mass = orc.t5_dtable(ref[5].abs(), M, N, not causal)                       # |dS| flowing into each bucket
-    for skip in levels:
-        err = (outs[skip][4].t().double().cpu() - dt_ref).norm() / mass.norm()
-        assert err < 4e-3, (skip, float(err))
+    for route in levels:
+        err = (outs[route][4].t().double().cpu() - dt_ref).norm() / mass.norm()
+        assert err < 4e-3, (route, float(err))
 
 
 @pytest.mark.gpu

@@ -137,32 +137,3 @@ def test_bias_feeds_attention_end_to_end():
     dt_ref.index_add_(0, bk.reshape(-1), ref[5][0].permute(1, 2, 0).reshape(-1, H))
     mx, rf = orc.error_metrics(dtable, dt_ref)
     assert rf < 1.2e-2, (mx, rf)                                                      # inherits the dBias 16-bit tolerance
-
-
-@pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("B200T5_T5BIAS_TILES_GPU") != "1",
-                    reason="developer variant of the producer backward (tile-parallel diagonal walk) not yet run on hardware")
-@pytest.mark.parametrize("H,M,N,bidir,dt", [(4, 512, 512, True, torch.bfloat16), (3, 300, 700, True, torch.float16),
-                                            (2, 1000, 130, False, torch.bfloat16)])
-def test_cuda_tile_parallel_backward_matches_default(H, M, N, bidir, dt):
-    """B200T5_T5BIAS_BWD_TILES=1: the table gradient of a dense 16-bit dBias through rpe_dtable_band_kernel (every tile)
-    against the default row-band kernel; both sum in fp32, so they agree to summation order."""
-    from flasht5_b200.positional_encoding import t5_bias_bwd
-    g = torch.Generator().manual_seed(H * M + N)
-    pe = RelativePositionalEncoding(32, 128, H, max(M, N), bidirectional=bidir)
-    lut = pe._bucket_lut(-(M - 1), N - 1, "cuda:0")
-    dbias = torch.randn(1, H, M, N, generator=g).to("cuda:0", dt)
-    outs = {}
-    old = os.environ.get("B200T5_T5BIAS_BWD_TILES")
-    try:
-        for flag in ("0", "1"):
-            os.environ["B200T5_T5BIAS_BWD_TILES"] = flag
-            outs[flag] = t5_bias_bwd(dbias, lut, M - 1, None, None, 32)
-            torch.cuda.synchronize()
-    finally:
-        if old is None:
-            os.environ.pop("B200T5_T5BIAS_BWD_TILES", None)
-        else:
-            os.environ["B200T5_T5BIAS_BWD_TILES"] = old
-    mx, rf = orc.error_metrics(outs["1"], outs["0"].double())
-    assert rf < 1e-5, (mx, rf)

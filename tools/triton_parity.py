@@ -119,12 +119,11 @@ def oracle_fp64(q, k, v, bias, do, causal, scale, need_bwd):
                 dq[b, sl] = torch.matmul(ds, kb) * scale
                 dk[b, sl] = torch.matmul(ds.transpose(1, 2), qb) * scale
                 if db is not None:
-                    if bias.shape[0] > 1:
-                        db[b, sl] += ds
-                    elif bias.shape[1] > 1:
-                        db[0, sl] += ds
+                    bi = b if bias.shape[0] > 1 else 0
+                    if bias.shape[1] > 1:
+                        db[bi, sl] += ds
                     else:
-                        db[0, 0] += ds.sum(0)
+                        db[bi, 0] += ds.sum(0)
     return o, dq, dk, dv, db
 
 
