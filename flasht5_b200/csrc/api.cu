@@ -415,7 +415,7 @@ static int attn_bwd_impl(const b200t5_attn_params* p, const b200t5_rpe_params* r
     // delta, zero-fill of the dQ group surface and (when dS is reduce-added) of the dS group surface -- and, for the v3 kernel
     // with a dense bias, the repacked bias copy -- in one launch
     const int m_pad = (p->M + 127) / 128 * 128;
-    float* nl = delta;                                                              // v3: [nl | ndelta]
+    float* nl = delta;                                                              // v3: records of [64 x nl | 64 x -delta] per 64 padded rows
     float* ndelta = reinterpret_cast<float*>(ws + w.dq_off / 2);
     cudaError_t e;
     if (w.transposed)
@@ -431,7 +431,7 @@ static int attn_bwd_impl(const b200t5_attn_params* p, const b200t5_rpe_params* r
     const uint32_t boxd = p->D >= 64 ? 64 : p->D;
     AttnBwdKernelParams kp;
     memset(&kp, 0, sizeof(kp));
-    const uint32_t qrows = w.transposed ? 32 : 128;         // the v3 kernel loads Q / dO per 32-query sub-tile
+    const uint32_t qrows = w.transposed ? 64 : 128;         // the v3 kernel loads Q / dO per 64-query half tile
     if ((rc = make_map_4d(&kp.map_q, p->q, 2, dt, p->D, p->M, p->H, p->B, p->q_strides[2], p->q_strides[1], p->q_strides[0], boxd, qrows, "q"))) return rc;
     if ((rc = make_map_4d(&kp.map_k, p->k, 2, dt, p->D, p->N, p->H, p->B, p->k_strides[2], p->k_strides[1], p->k_strides[0], boxd, 128, "k"))) return rc;
     if ((rc = make_map_4d(&kp.map_v, p->v, 2, dt, p->D, p->N, p->H, p->B, p->v_strides[2], p->v_strides[1], p->v_strides[0], boxd, 128, "v"))) return rc;

@@ -591,18 +591,21 @@ __device__ __forceinline__ void attn_bwd_preprocess_body(const uint8_t* __restri
         if (nl_out == nullptr) {
             delta[row] = acc;
         } else {
-            const int64_t prow = (row / M) * m_pad + (row % M);
+            // one 512-byte record per 64 padded rows: [64 x nl | 64 x -delta] (the kernel fetches a record with one bulk copy)
+            const int mm = static_cast<int>(row % M);
+            const int64_t prow = (row / M) * (2 * (int64_t)m_pad) + (mm >> 6) * 128 + (mm & 63);
             const float Lv = __ldg(lse + row);
             nl_out[prow] = Lv < -1e37f ? -INFINITY : -Lv * 1.4426950408889634f;
-            delta[prow] = -acc;
+            nl_out[prow + 64] = -acc;
         }
     }
     if (nl_out != nullptr && m_pad > M) {
         const int64_t pad = m_pad - M, total = (int64_t)B * H * pad;
         for (int64_t i = gid; i < total; i += (int64_t)vgrid * blockDim.x) {
-            const int64_t prow = (i / pad) * m_pad + M + (i % pad);
+            const int mm = M + static_cast<int>(i % pad);
+            const int64_t prow = (i / pad) * (2 * (int64_t)m_pad) + (mm >> 6) * 128 + (mm & 63);
             nl_out[prow] = -INFINITY;
-            delta[prow] = 0.f;
+            nl_out[prow + 64] = 0.f;
         }
     }
     // zero-fill of the dS batch-group surface (replaces a separate memset node)

@@ -64,26 +64,34 @@ constexpr int kNSub = kBM / kSub;   // 4
 constexpr int kBoxBytes = 128 * kSub * 2;   // [128 keys][32 queries] 16-bit, 64B-swizzled rows
 constexpr float kLog2e = 1.4426950408889634f;
 
-template <int kD>
+template <int kD, int kBiasMode>
 struct Bwd3Cfg {
     static_assert(kD == 16 || kD == 32 || kD == 64, "v3 backward covers head dims 16, 32, 64");
     static constexpr int kRowBytes = kD * 2;
     static constexpr int kTileBytes = 128 * kD * 2;
     static constexpr int kSubTileBytes = kSub * kD * 2;
     static constexpr uint32_t kSwizzle = kRowBytes == 128 ? kSwz128 : (kRowBytes == 64 ? kSwz64 : kSwz32);
-    // Q / dO ring: one slot = the 32 query rows of one sub-tile (Q rows + dO rows).  11 slots = almost three tiles of look-ahead: a
-    // slot is released as soon as the dV / dK MMAs of its sub-tile complete, so the producer runs ~2.5 tiles ahead (a ring of
-    // two whole tiles released after dQ(k) left the first sub-tile of every other tile waiting ~2 400 cycles for its TMA)
-    static constexpr int kSlots = 11;
+    // Q / dO ring: one slot = the 64 query rows of two sub-tiles (Q rows + dO rows + their row statistics: three TMA operations).
+    // A slot is released when the dV / dK MMAs of both its sub-tiles complete -- after the compute warps are through with them, so
+    // a slot lives ~5 700 cycles (TMA issue + flight 1 500, S^T MMAs 500, math 2 500, dV / dK MMAs 700) and the ring depth sets the
+    // ring must hold > 2 tiles.  5 slots; 7 without a bias, where the 32 KB of bias staging / band are not needed (measured: no
+    // faster -- the ring is not the pacemaker any more; staging the bias inside the dS^T boxes to get 7 slots with a bias
+    // cost 100 us: the boxes then have to be free a whole tile earlier).  (A ring of
+    // two whole tiles left the first sub-tile of every other tile waiting ~2 400 cycles for its TMA; a ring of eleven 32-row
+    // slots made the single producer lane the pacemaker of the whole CTA: 4 operations + a probe = ~650 cycles per sub-tile,
+    // 2 600 per tile against 1 500 of math -- profiles/r2c_bwd_v3_timeline_*.)
+    static constexpr int kSlots = kBiasMode == 0 ? 7 : 5;
+    static constexpr int kSlotRows = 2 * kSub;
+    static constexpr int kSlotBytes = 2 * kSubTileBytes;
     static constexpr int kK = 0;
     static constexpr int kQ = kK + kTileBytes;
-    static constexpr int kDO = kQ + kSlots * kSubTileBytes;
-    static constexpr int kDS = kDO + kSlots * kSubTileBytes;           // [2 tiles][4 boxes] dS^T
-    static constexpr int kDQ = kDS + 2 * kNSub * kBoxBytes;            // dQ staging tile [128][D] io dtype
-    static constexpr int kBand = kDQ + kTileBytes;                     // relative-position band (mode 3), <= 32 KB
-    static constexpr int kStats = kBand + 32768;                       // [kSlots][2][32] fp32: -L*log2e, -delta of the slot's queries
-    static constexpr int kBars = kStats + kSlots * 2 * kSub * 4;
-    static constexpr int kNumBars = 2 + 2 * kSlots + 6 * kNSub + 3 + 2;
+    static constexpr int kDO = kQ + kSlots * kSlotBytes;
+    static constexpr int kDS = kDO + kSlots * kSlotBytes;              // [2 tiles][4 boxes] dS^T
+    static constexpr int kDQ = kDS + 2 * kNSub * kBoxBytes;            // dQ staging tile [128][D] io dtype (prologue: the V tile)
+    static constexpr int kBand = kDQ + kTileBytes;                     // relative-position band (mode 3) / bias staging (mode 1), 32 KB
+    static constexpr int kStats = kBand + (kBiasMode == 0 ? 0 : 32768);                     // [kSlots][2][64] fp32: -L*log2e, -delta of the slot's queries
+    static constexpr int kBars = kStats + kSlots * 2 * kSlotRows * 4;
+    static constexpr int kNumBars = 2 + 2 * kSlots + 6 * kNSub + 3 + 2 + 2;
     static constexpr int kTmemSlot = kBars + kNumBars * 8;
     static constexpr int kTotal = kTmemSlot + 16;
     static_assert(kTotal <= 232448, "shared memory budget");
@@ -129,6 +137,10 @@ template <bool kBf16, int kBiasMode, bool kMask, bool kConst, bool kSum>
 __device__ __forceinline__ void v3_chunk(const uint32_t (&sr)[16], const uint32_t (&dr)[16], const float* nl, const float* nd,
                                          const uint32_t* bw, const float* bp, float bconst, float scale_log2, int vis_lo,
                                          uint32_t* pp, uint32_t* dd, float& ds_sum) {
+#ifdef B200T5_DBG_SKIP_MATH
+    for (int c = 0; c < 8; ++c) { pp[c] = sr[2 * c]; dd[c] = dr[2 * c + 1]; }
+    return;
+#endif
     const f32x2 sc2 = f2_pack(scale_log2, scale_log2);
     const f32x2 l2e2 = f2_pack(kLog2e, kLog2e);
     f32x2 sum2 = f2_pack(0.f, 0.f);
@@ -164,8 +176,13 @@ __device__ __forceinline__ void v3_chunk(const uint32_t (&sr)[16], const uint32_
             const f32x2 ds2 = f2_mul(p2, f2_add(f2_pack_bits(dr[c], dr[c + 1]), f2_pack(ndv[2 * e], ndv[2 * e + 1])));
             float g0, g1;
             f2_unpack(ds2, g0, g1);
+#ifdef B200T5_DBG_TRUNC_PACK
+            pp[c / 2] = __byte_perm(__float_as_uint(p0), __float_as_uint(p1), 0x7632);
+            dd[c / 2] = __byte_perm(__float_as_uint(g0), __float_as_uint(g1), 0x7632);
+#else
             pp[c / 2] = pack2<kBf16>(p0, p1);
             dd[c / 2] = pack2<kBf16>(g0, g1);
+#endif
             if (kSum) sum2 = f2_add(sum2, ds2);
         }
     }
@@ -195,7 +212,7 @@ constexpr int kWarpDrain0 = 16, kWarpTma = 20, kWarpMmaA = 21, kWarpMmaB = 22, k
 template <int kD, bool kBf16, int kBiasMode, bool kCausal>
 __global__ void __launch_bounds__(kThreads, 1)     // 72 registers per thread at launch: a pool of 896 x 72 = 64 512 for setmaxnreg
 attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
-    using C = Bwd3Cfg<kD>;
+    using C = Bwd3Cfg<kD, kBiasMode>;
     extern __shared__ __align__(1024) uint8_t smem[];
 
     const int warp = threadIdx.x >> 5;
@@ -237,6 +254,7 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
     uint64_t* dq_full = dp_empty + kNSub;
     uint64_t* dq_empty = dq_full + 1;
     uint64_t* all_done = dq_empty + 1;                  // every MMA of the CTA completed (single phase: the epilogue's gate; B and C commit)
+    uint64_t* b_turn = all_done + 3;                    // [2] B0 <-> B1 token: the dV / dK MMAs are issued in sub-tile order (bitwise reproducible sums)
     uint64_t* box_free = all_done + 1;                  // [2] dS^T boxes of tile parity: dQ MMAs done + TMA reduce reads done (C -> compute)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::kTmemSlot);
 
@@ -246,11 +264,13 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
         mbar_init(kt_ready, 4);
         for (int i = 0; i < C::kSlots; ++i) {
             mbar_init(qdo_full + i, 1);
-            mbar_init(qdo_empty + i, 1);
+            mbar_init(qdo_empty + i, 2);                  // one commit from each B warp (the slot's even and odd sub-tile)
         }
         mbar_init(all_done, 3);                           // the two B warps and warp C
         mbar_init(box_free + 0, 2);
         mbar_init(box_free + 1, 2);
+        mbar_init(b_turn + 0, 1);
+        mbar_init(b_turn + 1, 1);
         for (int i = 0; i < kNSub; ++i) {
             mbar_init(sdp_full + i, 1);
             mbar_init(pds_full + i, 128);                 // every thread of compute warpgroup i arrives by itself
@@ -283,22 +303,24 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
         constexpr uint32_t hi_op = sdesc_hi(sbo, C::kSwizzle);       // Q, dO, K tiles (either major)
         if (warp == kWarpTma && lane == 0 && n_iter > 0) {
             // ---- K once; then the Q / dO ring (one slot = the 32 query rows of one sub-tile) ----
-            mbar_arrive_expect_tx(k_full, C::kTileBytes);
+            // (V lands in the dQ staging tile, which is idle until the first dQ is drained: the drain warpgroup copies both
+            //  tiles into TMEM)
+            mbar_arrive_expect_tx(k_full, 2 * C::kTileBytes);
             tma_load_4d(smem + C::kK, &p.map_k, k_full, 0, col0, h, b);
-            for (int t = 0; t < T; ++t) {
-                const int s = t % C::kSlots;
-                const int m0 = (i_start + (t >> 2)) * kBM + (t & 3) * kSub;
-                BWD3_TS(7, t, 0);
-                mbar_wait_producer(qdo_empty + s, ((t / C::kSlots) & 1) ^ 1);
-                BWD3_TS(7, t, 1);
-                mbar_arrive_expect_tx(qdo_full + s, 2 * C::kSubTileBytes + 2 * kSub * 4);
-                tma_load_4d(smem + C::kQ + s * C::kSubTileBytes, &p.map_q, qdo_full + s, 0, m0, h, b);
-                tma_load_4d(smem + C::kDO + s * C::kSubTileBytes, &p.map_do, qdo_full + s, 0, m0, h, b);
-                // row statistics of the 32 queries (padded rows: always in range, 128-byte aligned)
-                float* st = reinterpret_cast<float*>(smem + C::kStats) + s * (2 * kSub);
-                const int64_t srow = ((int64_t)b * p.H + h) * p.m_pad + m0;
-                bulk_load_1d(st, p.nl + srow, kSub * 4, qdo_full + s);
-                bulk_load_1d(st + kSub, p.ndelta + srow, kSub * 4, qdo_full + s);
+            tma_load_4d(smem + C::kDQ, &p.map_v, k_full, 0, col0, h, b);
+            const float* stat_bh = p.nl + ((int64_t)b * p.H + h) * (2 * (int64_t)p.m_pad);
+            for (int u = 0; u < 2 * n_iter; ++u) {
+                const int s = u % C::kSlots;
+                const int m0 = (i_start + (u >> 1)) * kBM + (u & 1) * C::kSlotRows;
+                BWD3_TS(7, u, 0);
+                mbar_wait_producer(qdo_empty + s, ((u / C::kSlots) & 1) ^ 1);
+                BWD3_TS(7, u, 1);
+                mbar_arrive_expect_tx(qdo_full + s, 2 * C::kSlotBytes + 2 * C::kSlotRows * 4);
+                tma_load_4d(smem + C::kQ + s * C::kSlotBytes, &p.map_q, qdo_full + s, 0, m0, h, b);
+                tma_load_4d(smem + C::kDO + s * C::kSlotBytes, &p.map_do, qdo_full + s, 0, m0, h, b);
+                // row statistics of the 64 queries: [-L * log2e | -delta], one 512-byte record per 64 padded rows
+                bulk_load_1d(reinterpret_cast<float*>(smem + C::kStats) + s * (2 * C::kSlotRows), stat_bh + (m0 / C::kSlotRows) * (2 * C::kSlotRows),
+                             2 * C::kSlotRows * 4, qdo_full + s);
             }
         } else if ((warp == kWarpMmaA || warp == kWarpMmaA1 || warp == kWarpMmaA2 || warp == kWarpMmaA3) && n_iter > 0) {
             // ---- MMA warp A: S^T = K Q^T and dP^T = V dO^T of every sub-tile (A operands K, V in TMEM) ----
@@ -314,7 +336,8 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
             for (int t = j_mine; t < T; t += kNSub) {
                 const int k = t >> 2, j = t & 3;
                 if (lane == 0) BWD3_TS(6, t, 0);
-                mbar_wait(qdo_full + (t % C::kSlots), (t / C::kSlots) & 1);
+                const int u = t >> 1;                                   // half-tile = ring slot use
+                mbar_wait(qdo_full + (u % C::kSlots), (u / C::kSlots) & 1);
                 if (lane == 0) BWD3_TS(6, t, 1);
                 if (t >= 2) {
                     // buffer t & 1 held sub-tile t - 2 (warpgroup (j + 2) & 3, tile (t - 2) >> 2): in registers by now?
@@ -324,7 +347,7 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
                 }
                 tc_fence_after();
                 if (lane == 0) BWD3_TS(6, t, 2);
-                const uint32_t so = (t % C::kSlots) * (C::kSubTileBytes >> 4);
+                const uint32_t so = ((u % C::kSlots) * 2 + (t & 1)) * (C::kSubTileBytes >> 4);
                 const uint32_t tm_s = tmem_base + C::kColS + (t & 1) * kSub;
                 const uint32_t tm_dp = tmem_base + C::kColDP + (t & 1) * kSub;
                 if (leader) {
@@ -355,9 +378,13 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
                 mbar_wait(pds_full + (k & 1) * kNSub + j, (k >> 1) & 1);
                 tc_fence_after();
                 if (lane == 0) BWD3_TS(4, t, 1);
-                const uint32_t so = (t % C::kSlots) * (C::kSubTileBytes >> 4);
+                const int slot = (t >> 1) % C::kSlots;
+                const uint32_t so = (slot * 2 + (t & 1)) * (C::kSubTileBytes >> 4);
                 const uint32_t tm_p = tmem_base + C::kColP + j * 16;         // P^T  (packed 16-bit pairs)
                 const uint32_t tm_ds = tmem_base + C::kColDS + j * 16;       // dS^T (packed 16-bit pairs)
+                // the other B warp has issued sub-tile t - 1: both accumulate into the same dV / dK columns, and a fixed order
+                // of the fp32 additions makes dK, dV bitwise reproducible (strict alternation: nobody lags a phase)
+                if (t > 0) mbar_wait(b_turn + (t & 1), ((t - 1) >> 1) & 1);
                 if (leader) {
                     // (K dimension = the 32 queries of this sub-tile)
 #pragma unroll
@@ -369,8 +396,9 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
                     umma_commit(pds_free + j);
                     // Q / dO slot: the S^T / dP^T MMAs of warp A that read it completed before the compute warps could produce
                     // the P^T this warp just consumed, so this commit covers every reader of the slot
-                    umma_commit(qdo_empty + (t % C::kSlots));
+                    umma_commit(qdo_empty + slot);
                     if (t >= T - 2) umma_commit(all_done);          // the last sub-tile of this warp (T is a multiple of 4)
+                    mbar_arrive(b_turn + ((t + 1) & 1));
                 }
                 __syncwarp();
                 if (lane == 0) BWD3_TS(4, t, 3);
@@ -430,7 +458,7 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
                 }
                 __syncwarp();
             }
-            if (leader) bulk_wait_group<0>();                       // every store / reduction of this CTA has landed
+            if (leader) bulk_wait_group_read<0>();                  // shared memory must outlive the reads; the writes complete by themselves
         }
     } else if (warp >= kWarpDrain0) {
         // =============================== drain warpgroup (16..19) ===============================
@@ -438,31 +466,22 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
         const int r = (warp & 3) * 32 + lane;                 // TMEM lane
         const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
         if (n_iter > 0) {
-            // ---- prologue: K and V rows of this key block -> TMEM (the A operands of S^T and dP^T) ----
-            const int gn = col0 + r;
+            // ---- prologue: K and V rows of this key block, shared memory (TMA, swizzled rows) -> TMEM (the A operands of
+            //      S^T and dP^T).  Reading them from global memory here cost ~4 000 cycles per CTA (56 registers: the loads
+            //      of a row went out in small batches, each one a trip to HBM) ----
+            mbar_wait(k_full, 0);
+            const int sw = kD == 64 ? (r & 7) : (kD == 32 ? ((r >> 1) & 3) : ((r >> 2) & 1));   // 16-byte chunk ^= f(row)
 #pragma unroll
             for (int which = 0; which < 2; ++which) {
-                const uint8_t* base = reinterpret_cast<const uint8_t*>(which == 0 ? p.k : p.v);
-                const int64_t off = which == 0 ? ((int64_t)b * p.k_sb + (int64_t)h * p.k_sh + (int64_t)gn * p.k_sn)
-                                               : ((int64_t)b * p.v_sb + (int64_t)h * p.v_sh + (int64_t)gn * p.v_sn);
-                const uint4* src = reinterpret_cast<const uint4*>(base + 2 * off);
+                const uint8_t* row = smem + (which == 0 ? C::kK : C::kDQ) + r * C::kRowBytes;
                 const uint32_t tm_dst = tmem_base + lane_off + (which == 0 ? C::kColKt : C::kColVt);
 #pragma unroll
                 for (int i = 0; i < kD / 16; ++i) {                    // 8 words (16 elements) at a time
-                    uint4 a = make_uint4(0, 0, 0, 0), c = make_uint4(0, 0, 0, 0);
-                    if (gn < p.N) {
-                        a = __ldg(src + 2 * i);
-                        c = __ldg(src + 2 * i + 1);
-                    }
+                    const uint4 a = *reinterpret_cast<const uint4*>(row + (((2 * i) ^ sw) << 4));
+                    const uint4 c = *reinterpret_cast<const uint4*>(row + (((2 * i + 1) ^ sw) << 4));
                     const uint32_t w[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
                     tmem_st8(tm_dst + 8 * i, w);
                 }
-            }
-            {
-                // dV, dK accumulators start at zero (every dV / dK MMA accumulates: two warps issue them)
-                const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-                for (int c = 0; c < 2 * kD; c += 8) tmem_st8(tmem_base + lane_off + C::kColDV + c, z);
             }
             tmem_st_wait();
             tc_fence_before();
@@ -508,7 +527,7 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
             }
             if (r == 0) BWD3_TS(5, k, 2);
         }
-        if (r == 0) bulk_wait_group<0>();
+        if (r == 0) bulk_wait_group_read<0>();
     } else {
         // =============================== compute warpgroups 0..3 (warps 0..15) ===============================
         setmaxnreg_inc<96>();     // the CTA owns 896 x 72 = 64 512 registers (its launch allocation): 512 x 96 + 128 x 56 (drain) + 256 x 32 (control)
@@ -545,12 +564,19 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
         // The 64 bytes of bias this thread needs for its next sub-tile are copied global -> shared with cp.async (no registers:
         // they would be live across a whole sub-tile) into the band's shared memory (mode 3 is the other user): [wg][chunk][row].
         uint4* const bias_stage = reinterpret_cast<uint4*>(smem + C::kBand) + wg * (4 * 128) + r;
-        auto load_bias = [&](int m0) {
-            const uint4* src = bias_blk + (int64_t)(m0 / kSub) * (4 * 128);
+        auto load_bias = [&](int kk) {                          // kk: tile (iteration) whose bias is fetched
+            const uint4* src = bias_blk + (int64_t)(((i_start + kk) * kBM + wg * kSub) / kSub) * (4 * 128);
 #pragma unroll
             for (int c = 0; c < 4; ++c) cp_async_16(bias_stage + c * 128, src + c * 128);
         };
-        if (n_iter > 0 && kBiasMode == 1) load_bias(i_start * kBM + wg * kSub);
+        if (n_iter > 0 && kBiasMode == 1) load_bias(0);
+        if (wg == 0 && n_iter > 0) {
+            // dV, dK accumulators start at zero: every dV / dK MMA accumulates (two warps issue them).  Ordered before the first
+            // of those MMAs by this warpgroup's first pds_full arrival (tcgen05.wait::st + fence come first) and the B0 -> B1 token.
+            const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+            for (int c = 0; c < 2 * kD; c += 8) tmem_st8(tmem_base + lane_off + C::kColDV + c, z);
+        }
 
         for (int k = 0; k < n_iter; ++k) {
             const int m0 = (i_start + k) * kBM + wg * kSub;
@@ -585,6 +611,7 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
             tmem_ld32(tm_s, sr);
             tmem_ld32(tm_dp, drr);
             tmem_ld_wait();
+            if (r == 0) BWD3_TS(wg, k, 4);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(s_empty + wg);
@@ -599,8 +626,8 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
                 }
                 const uint32_t(&dr)[16] = *reinterpret_cast<const uint32_t(*)[16]>(drr + hc * 16);
                 // statistics of the slot: the S^T MMAs of this sub-tile were issued after warp A saw the slot's barrier complete
-                const float* nl = reinterpret_cast<const float*>(smem + C::kStats) + ((4 * k + wg) % C::kSlots) * (2 * kSub) + hc * 16;
-                const float* nd = nl + kSub;
+                const float* nl = reinterpret_cast<const float*>(smem + C::kStats) + (((4 * k + wg) >> 1) % C::kSlots) * (2 * C::kSlotRows) + (wg & 1) * kSub + hc * 16;
+                const float* nd = nl + C::kSlotRows;
                 // bias mode 3, element c of this half: band[(gn - (m0 + 16 hc + c)) - band_lo]
                 const float* bp = band + (gn - m0 - hc * 16 - p.rpe.band_lo);
                 const int vl = vis_lo - hc * 16;
@@ -620,24 +647,26 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
                     if (need_mask) v3_chunk<kBf16, kBiasMode, true, false, false>(srh, dr, nl, nd, bw, bp, 0.f, scale_log2, vl, pp, dd, dummy);
                     else v3_chunk<kBf16, kBiasMode, false, false, false>(srh, dr, nl, nd, bw, bp, 0.f, scale_log2, 0, pp, dd, dummy);
                 }
+                if (r == 0) BWD3_TS(wg, k, 5 + hc);                  // (5: first half computed, 6: second half computed)
                 if (hc == 0 && k > 0) {
                     mbar_wait(pds_free + wg, (k - 1) & 1);        // dV,dK of this warpgroup's previous sub-tile have read P^T / dS^T
                     // the dS^T box (tile parity, j) was last used two tiles ago: its dQ MMAs and its TMA reduce have read it
                     if (k >= 2) mbar_wait(box_free + (k & 1), ((k >> 1) - 1) & 1);
                     tc_fence_after();
                 }
+                if (r == 0 && hc == 0) BWD3_TS(wg, k, 7);             // (7: P^T / dS^T buffers and the box are free)
                 tmem_st8(tm_p + hc * 8, pp);
                 tmem_st8(tm_ds + hc * 8, dd);
                 *reinterpret_cast<uint4*>(sDS + (((2 * hc) ^ rx) << 4)) = make_uint4(dd[0], dd[1], dd[2], dd[3]);
                 *reinterpret_cast<uint4*>(sDS + (((2 * hc + 1) ^ rx) << 4)) = make_uint4(dd[4], dd[5], dd[6], dd[7]);
             }
             if (r == 0) BWD3_TS(wg, k, 2);
-            if (kBiasMode == 1 && k + 1 < n_iter) load_bias(m0 + kBM);     // lands during the wait for the next S^T
             tmem_st_wait();
             tc_fence_before();
             fence_proxy_async_smem();
             mbar_arrive(pds_full + (k & 1) * kNSub + wg);
             if (r == 0) BWD3_TS(wg, k, 3);
+            if (kBiasMode == 1 && k + 1 < n_iter) load_bias(k + 1);       // lands during the wait for the next S^T
         }
 
         // ---- tail: constant-tile sums; then dV (warpgroups 0, 1: D/2 columns each) and dK * sm_scale (warpgroups 2, 3) ----
@@ -703,7 +732,7 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
 // ------------------------------------------------------------------------------------------
 template <int kD, bool kBf16, int kBiasMode, bool kCausal>
 static cudaError_t launch_bwd3_inst(const AttnBwdKernelParams& kp, cudaStream_t stream) {
-    using C = Bwd3Cfg<kD>;
+    using C = Bwd3Cfg<kD, kBiasMode>;
     auto kern = attn_bwd_kernel_v3<kD, kBf16, kBiasMode, kCausal>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal);
     if (e != cudaSuccess) return e;
@@ -716,14 +745,14 @@ static cudaError_t launch_bwd3_inst(const AttnBwdKernelParams& kp, cudaStream_t 
         static long long ts[8][32][8];
         cudaMemcpyFromSymbol(ts, g_bwd3_ts, sizeof(ts));
         const long long t0 = ts[0][0][0];
-        const char* names[8] = {"wg0 [wait S, S ready, math done, stored + signalled]  (per tile)", "wg1", "wg2", "wg3",
+        const char* names[8] = {"wg0 [wait S, S ready, math done, stored + signalled | S in registers, half 0 computed, half 1 computed, buffers free]  (per tile)", "wg1", "wg2", "wg3",
                                 "mma B [wait P/dS(t), ready, dq gate (warp C), issued]  (per sub-tile)", "drain [wait dQ, dQ ready, reduce issued]  (per tile)",
                                 "mma A [wait Q/dO slot, slot ready, buffers free, issued]  (per sub-tile)", "producer [wait slot empty, empty]  (per sub-tile)"};
         for (int role = 0; role < 8; ++role) {
             printf("BWD3_TIMING %s\n", names[role]);
             for (int k = 0; k < ((role == 4 || role >= 6) ? 32 : 8); ++k) {
                 printf("  %2d:", k);
-                for (int j = 0; j < 4; ++j) printf(" %7lld", ts[role][k][j] ? ts[role][k][j] - t0 : 0);
+                for (int j = 0; j < (role < 4 ? 8 : 4); ++j) printf(" %7lld", ts[role][k][j] ? ts[role][k][j] - t0 : 0);
                 printf("\n");
             }
         }
