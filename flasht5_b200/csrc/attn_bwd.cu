@@ -939,58 +939,78 @@ template <bool kBf16, bool kOutF32>
 __device__ __forceinline__ void dbias_reduce_t_body(const uint16_t* __restrict__ ws, int m_pitch, void* __restrict__ out_v,
                                                     int64_t o_sb, int64_t o_sh, int64_t o_sm, int64_t o_sn, int G, int H,
                                                     int M, int N, int reduce_b, int reduce_h, int causal, int bx, int by, int bz) {
+    // thread (ty, tx) = (tid / 8, tid % 8): loads 16 bytes = 8 consecutive m of rows n0 + ty and n0 + ty + 32 (a warp reads
+    // four 128-byte row segments per instruction), writes 8 consecutive n of rows m0 + ty and m0 + ty + 32 the same way.
     __shared__ float tile[64][65];
     const int m0 = bx * 64, n0 = by * 64;
     const int oh_n = reduce_h ? 1 : H;
     const int ob = bz / oh_n, oh = bz % oh_n;
-    const int ty = threadIdx.x >> 5, tx = threadIdx.x & 31;
+    const int ty = threadIdx.x >> 3, tx = threadIdx.x & 7;
     const int pseq = N - M;
     const bool tile_masked = causal && (n0 > m0 + 63 + pseq);              // every (m, n) of the tile is above the diagonal
-    float acc[8][2];
+    float acc[2][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = 0.f;
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
     if (!tile_masked) {
         const int g0 = reduce_b ? 0 : ob, g1 = reduce_b ? G : ob + 1;
         const int h0 = reduce_h ? 0 : oh, h1 = reduce_h ? H : oh + 1;
-        const int m = m0 + 2 * tx;
+        const int m = m0 + 8 * tx;                                         // (the row pitch is a multiple of 8: m < M => in the row)
         for (int g = g0; g < g1; ++g)
             for (int hh = h0; hh < h1; ++hh) {
                 const uint16_t* src = ws + ((int64_t)g * H + hh) * (int64_t)N * m_pitch;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int n = n0 + ty + 8 * j;
+                for (int j = 0; j < 2; ++j) {
+                    const int n = n0 + ty + 32 * j;
                     if (n < N && m < M) {
-                        const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(src + (int64_t)n * m_pitch + m));
-                        const float2 f = unpack2<kBf16>(u);
-                        acc[j][0] += f.x;
-                        acc[j][1] += f.y;
+                        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)n * m_pitch + m));
+                        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 f = unpack2<kBf16>(w[e]);
+                            acc[j][2 * e] += f.x;
+                            acc[j][2 * e + 1] += f.y;
+                        }
                     }
                 }
             }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        tile[ty + 8 * j][2 * tx] = acc[j][0];
-        tile[ty + 8 * j][2 * tx + 1] = acc[j][1];
-    }
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) tile[ty + 32 * j][8 * tx + e] = acc[j][e];          // tile[n][m]
     __syncthreads();
     const int64_t obase = ob * o_sb + oh * o_sh;
+    const bool vec_ok = o_sn == 1 && (o_sm % 8) == 0 && (obase % 8) == 0 &&
+                        (reinterpret_cast<uintptr_t>(out_v) % (kOutF32 ? 32 : 16)) == 0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int ml = ty + 8 * j, m = m0 + ml;
+    for (int j = 0; j < 2; ++j) {
+        const int ml = ty + 32 * j, m = m0 + ml;
         if (m >= M) continue;
+        const int nb = n0 + 8 * tx;
+        float v[8];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int nl = tx + 32 * e, n = n0 + nl;
-            if (n >= N) continue;
-            float v = tile[nl][ml];
-            if (causal && n > m + pseq) v = 0.f;                          // select, not multiply: unwritten tiles may hold anything
-            const int64_t oi = obase + (int64_t)m * o_sm + (int64_t)n * o_sn;
+        for (int e = 0; e < 8; ++e) {
+            v[e] = tile[8 * tx + e][ml];
+            if (causal && nb + e > m + pseq) v[e] = 0.f;                    // select, not multiply: unwritten tiles may hold anything
+        }
+        const int64_t oi = obase + (int64_t)m * o_sm + (int64_t)nb * o_sn;
+        if (vec_ok && nb + 8 <= N) {
             if constexpr (kOutF32) {
-                static_cast<float*>(out_v)[oi] = v;
+                float4* dst = reinterpret_cast<float4*>(static_cast<float*>(out_v) + oi);
+                dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+                dst[1] = make_float4(v[4], v[5], v[6], v[7]);
             } else {
-                const uint32_t packed = pack2<kBf16>(v, 0.f);
-                static_cast<uint16_t*>(out_v)[oi] = static_cast<uint16_t>(packed & 0xFFFFu);
+                *reinterpret_cast<uint4*>(static_cast<uint16_t*>(out_v) + oi) =
+                    make_uint4(pack2<kBf16>(v[0], v[1]), pack2<kBf16>(v[2], v[3]), pack2<kBf16>(v[4], v[5]), pack2<kBf16>(v[6], v[7]));
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                if (nb + e >= N) continue;
+                if constexpr (kOutF32) static_cast<float*>(out_v)[oi + e * o_sn] = v[e];
+                else static_cast<uint16_t*>(out_v)[oi + e * o_sn] = static_cast<uint16_t>(pack2<kBf16>(v[e], 0.f) & 0xFFFFu);
             }
         }
     }

@@ -323,11 +323,13 @@ def test_cuda_matches_reference_golden(path, fused):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape", [(2, 4, 512, 512, 64, False), (2, 4, 512, 512, 64, True), (1, 2, 300, 700, 128, False),
-                                   (2, 2, 640, 384, 32, True), (1, 3, 130, 130, 16, False), (3, 8, 1024, 1024, 64, False)],
+                                   (2, 2, 640, 384, 32, False), (2, 2, 384, 640, 32, True), (1, 3, 130, 130, 16, False), (3, 8, 1024, 1024, 64, False)],
                          ids=lambda s: "x".join(map(str, s)))
 def test_cuda_fused_equals_dense_operator(shape):
     """Same 16-bit bias values, same arithmetic: O and LSE-dependent outputs are bit-identical to the dense-bias
-    operator; dQ (and dTable) only differ by the order of 16-bit partial sums."""
+    operator; dQ (and dTable) only differ by the order of 16-bit partial sums.
+    (No causal case with M > N: there every visible position lies beyond max_distance, i.e. in ONE bucket, and the rows of dS
+    sum to zero -- the table gradient is rounding noise around 0 on both routes and a relative comparison says nothing.)"""
     from flasht5_b200 import flash_attention_v2_rpe
     B, H, M, N, D, causal = shape
     g = torch.Generator().manual_seed(11)
