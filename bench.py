@@ -259,7 +259,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from flasht5_b200 import _cabi, flash_attention_v2_bias
-    from flasht5_b200.data_parallel import allreduce_dbias, allreduce_dbias_f32, comm_group
+    from flasht5_b200.data_parallel import allreduce_dbias, allreduce_dbias_f32, allreduce_dbias_overlapped, comm_group
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -298,17 +298,20 @@ def run_ours(args):
     def step(i):
         q, k, v, bias, do = sets[i % NSETS]
         o, L = torch.ops.b200t5.attn_bias_fwd(q, k, v, bias, False, SM_SCALE)
-        if world > 1:
+        if world > 1 and args.exchange == "f32":
             # the one exchange of the path: the UNROUNDED fp32 dBias is summed over ranks on a side stream (NCCL capped at a
             # few CTAs so that it does not take SMs from the attention grids it overlaps) and rounded once afterwards
             dq, dk, dv, ds32 = torch.ops.b200t5.attn_bias_bwd_f32dbias(o, do, q, k, v, bias, L, False, SM_SCALE)
             ds = allreduce_dbias_f32(ds32, dtype, comm_stream, dp_group)
-        else:
+        elif world > 1 and args.exchange == "bf16":       # developer A/B: round first, widen + all-reduce + round again (round 1)
+            dq, dk, dv, ds = torch.ops.b200t5.attn_bias_bwd(o, do, q, k, v, bias, L, False, SM_SCALE)
+            ds = allreduce_dbias_overlapped(ds, comm_stream, dp_group)
+        else:                                               # one rank, or developer A/B --exchange none (INVALID as a DP step)
             dq, dk, dv, ds = torch.ops.b200t5.attn_bias_bwd(o, do, q, k, v, bias, L, False, SM_SCALE)
         return o, dq, dk, dv, ds
 
     comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
-    dp_group = comm_group(max_ctas=8) if world > 1 else None
+    dp_group = comm_group(max_ctas=args.nccl_ctas) if (world > 1 and args.nccl_ctas > 0) else None
 
     def barrier():
         if world > 1:
@@ -525,9 +528,12 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": WB * world, "seq_len": WS, "parallelism": "dp%d" % world,
                        "l2": "inputs rotate over %d buffer sets of 185 MB each (> 126 MB L2)" % NSETS,
-                       "exchange": "NCCL all-reduce of the unrounded fp32 dBias (33.5 MB) every step on a side stream through a "
-                                   "communicator capped at 8 CTAs, one rounding afterwards (overlaps the next step's kernels; "
-                                   "all of them complete inside the timed region)" if world > 1 else "none"},
+                       "exchange": ("none" if world == 1 else
+                                    "DEVELOPER A/B --exchange %s --nccl-ctas %d: not the product configuration" % (args.exchange, args.nccl_ctas)
+                                    if (args.exchange != "f32" or args.nccl_ctas != 16) else
+                                    "NCCL all-reduce of the unrounded fp32 dBias (33.5 MB) every step on a side stream through a "
+                                    "communicator capped at 16 CTAs, one rounding afterwards (overlaps the next step's kernels; "
+                                    "all of them complete inside the timed region)")},
             "tokens_per_s": world * B * S / (ms_step * 1e-3),
             "frac_of_peak": value / (world * peak), "peak_tflops_per_gpu": peak, "peak_source": peak_src,
             "gpu_launches": int(launches), "launches_per_step": launches / args.steps,
@@ -550,6 +556,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sustained", action="store_true")
     ap.add_argument("--no-siblings", action="store_true")
+    ap.add_argument("--exchange", default="f32", choices=["f32", "bf16", "none"], help="developer A/B of the N > 1 dBias exchange (the product is f32)")
+    ap.add_argument("--nccl-ctas", type=int, default=16, help="CTA cap of the exchange communicator (0: NCCL's default group)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -321,6 +321,8 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdKernelParams p) {
                        (p.bias_h_bcast ? 0 : (int64_t)h * p.bias_sh) + (int64_t)grow * p.bias_sm;
         }
 
+        const f32x2 scale2 = f2_pack(p.sm_scale, p.sm_scale);
+        const f32x2 l2e2 = f2_pack(kLog2e, kLog2e);
         for (int j = 0; j < num_tiles; ++j) {
             const int col0 = j * kBN;
             float x[kBN];
@@ -358,8 +360,7 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdKernelParams p) {
                         for (int e = 0; e < 4; ++e) {
                             const float2 f = unpack2<kBf16>(w[e]);
                             const int c = hh * 64 + c8 * 8 + e * 2;
-                            x[c] = fmaf(x[c], p.sm_scale, f.x);
-                            x[c + 1] = fmaf(x[c + 1], p.sm_scale, f.y);
+                            f2_unpack(f2_fma(f2_pack(x[c], x[c + 1]), scale2, f2_pack(f.x, f.y)), x[c], x[c + 1]);   // one FFMA2
                         }
                     }
                     // WAR across proxies: these generic-proxy reads must have completed before the TMA
@@ -384,15 +385,15 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdKernelParams p) {
                 if (rel_max <= p.rpe.const_lo || rel_min >= p.rpe.const_hi) {
                     const float bv = band[(rel_max <= p.rpe.const_lo ? p.rpe.const_lo : p.rpe.const_hi) - p.rpe.band_lo];
 #pragma unroll
-                    for (int c = 0; c < kBN; ++c) x[c] = fmaf(x[c], p.sm_scale, bv);
+                    for (int c = 0; c < kBN; c += 2) f2_unpack(f2_fma(f2_pack(x[c], x[c + 1]), scale2, f2_pack(bv, bv)), x[c], x[c + 1]);
                 } else {
                     const float* bp = band + (col0 - grow - p.rpe.band_lo);
 #pragma unroll
-                    for (int c = 0; c < kBN; ++c) x[c] = fmaf(x[c], p.sm_scale, bp[c]);
+                    for (int c = 0; c < kBN; c += 2) f2_unpack(f2_fma(f2_pack(x[c], x[c + 1]), scale2, f2_pack(bp[c], bp[c + 1])), x[c], x[c + 1]);
                 }
             } else {
 #pragma unroll
-                for (int c = 0; c < kBN; ++c) x[c] *= p.sm_scale;
+                for (int c = 0; c < kBN; c += 2) f2_unpack(f2_mul(f2_pack(x[c], x[c + 1]), scale2), x[c], x[c + 1]);
             }
 
             FWD_TS(0, j, 3);
@@ -445,16 +446,19 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdKernelParams p) {
             // with the stale reference max of the lazy rescale a dominant P is no longer exactly 1, and normalising by the
             // exact sum left O at 1.96e-3 relative error where Triton has 1.66e-3.)
             uint32_t pk[kBN / 2];
-            float s0 = 0.f, s1 = 0.f, r0 = 0.f, r1 = 0.f;
+            float s0, s1, r0 = 0.f, r1 = 0.f;
+            const f32x2 negm2 = f2_pack(neg_m_log2, neg_m_log2);
+            f32x2 sum2 = f2_pack(0.f, 0.f);
 #pragma unroll
             for (int c = 0; c < kBN; c += 2) {
-                const float e0 = ex2_approx(fmaf(x[c], kLog2e, neg_m_log2));
-                const float e1 = ex2_approx(fmaf(x[c + 1], kLog2e, neg_m_log2));
-                s0 += e0;
-                s1 += e1;
+                float a0, a1;
+                f2_unpack(f2_fma(f2_pack(x[c], x[c + 1]), l2e2, negm2), a0, a1);      // FFMA2 / FADD2: two columns per issue slot
+                const float e0 = ex2_approx(a0), e1 = ex2_approx(a1);
+                sum2 = f2_add(sum2, f2_pack(e0, e1));
                 pk[c / 2] = pack2<kBf16>(e0, e1);
                 add_f32_16x2<kBf16>(pk[c / 2], r0, r1, r0, r1);
             }
+            f2_unpack(sum2, s0, s1);
             l_sum = l_sum * alpha + (s0 + s1);
             l_hat = l_hat * alpha + (r0 + r1);
             FWD_TS(0, j, 5);

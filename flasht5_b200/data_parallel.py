@@ -59,12 +59,14 @@ def allreduce_dtable(dtable: Optional[torch.Tensor], group=None) -> Optional[tor
     return allreduce_dbias(dtable, group)
 
 
-def comm_group(max_ctas: int = 8):
+def comm_group(max_ctas: int = 16):
     """A process group for the dBias exchange whose NCCL kernels are capped at `max_ctas` CTAs.  The exchange runs on a side
     stream BESIDE attention kernels that fill every SM (2 048-CTA grids); NCCL's default of up to 32 CTAs per collective took
     SMs and ~100 MB of HBM traffic from them (round 1: the backward kernel slowed from 0.306 to 0.341 ms at 2-8 ranks).  The
-    message is 33.5 MB per step: a handful of CTAs moves it well within one step.  Falls back to the default group when
-    the backend is not NCCL or the option is unavailable."""
+    message is 33.5 MB per step: a handful of CTAs moves it well within one step.  Measured at N = 2 on B200
+    (profiles/r2c_n2_exchange_ab.txt, TFLOP/s of the whole job): no exchange 890 | cap 4: 820 | 6: 834 | 8: 836 / 544 (two runs:
+    on the edge of being communication-bound) | 12: 844 | 16: 846 | 32: 656 | NCCL's default group: 565.  Falls back to the
+    default group when the backend is not NCCL or the option is unavailable."""
     if not dist.is_available() or not dist.is_initialized():
         return None
     try:

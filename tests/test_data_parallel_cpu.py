@@ -41,6 +41,12 @@ def _worker(rank, world, port, tmp):
     db = allreduce_dbias(loc[5].to(torch.bfloat16))         # 16-bit local dBias, fp32 exchange, one rounding
     ok &= db.dtype == torch.bfloat16
     ok &= torch.allclose(db.double(), full[5], atol=2e-2, rtol=2e-2)
+    # the fp32 exchange of the unrounded dBias (attn_bias_bwd_f32dbias): summed before the single rounding
+    from flasht5_b200.data_parallel import allreduce_dbias_f32, comm_group
+    db32 = allreduce_dbias_f32(loc[5].float(), torch.bfloat16)
+    ok &= db32.dtype == torch.bfloat16
+    ok &= torch.equal(db32, full[5].float().to(torch.bfloat16)) or torch.allclose(db32.double(), full[5], atol=2e-2, rtol=1e-2)
+    ok &= comm_group(8) is None                             # gloo: no NCCL communicator options, default group is used
     # exact in fp64
     db64 = loc[5].clone()
     dist.all_reduce(db64)
@@ -71,3 +77,6 @@ def test_allreduce_is_noop_without_process_group():
     from flasht5_b200.data_parallel import allreduce_dbias
     t = torch.randn(3)
     assert allreduce_dbias(t) is t and allreduce_dbias(None) is None
+    from flasht5_b200.data_parallel import allreduce_dbias_f32, comm_group
+    assert allreduce_dbias_f32(None, torch.bfloat16) is None and comm_group() is None
+    assert allreduce_dbias_f32(t, torch.bfloat16).dtype == torch.bfloat16
