@@ -34,7 +34,10 @@ constexpr int kBiasStages = 2;
 constexpr int kBiasHalfBytes = kBM * 64 * 2;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
-constexpr float kRescaleThreshold = 8.0f * kLn2;   // keep a stale max while exp(x - m) <= 256
+// keep a stale reference max while exp(x - m) stays small enough for the io dtype of P: <= 2^8 for fp16 (max 65 504, and the
+// P V accumulation adds 128 of them), <= 2^16 for bf16 (fp32 exponent range; the fp32 accumulators are nowhere near overflow).
+// A larger bound means fewer O rescales in TMEM (~300 cycles per tile whenever one row of a warp needs it).
+template <bool kBf16> constexpr float kRescaleThreshold = (kBf16 ? 16.0f : 8.0f) * kLn2;
 
 template <int kD>
 struct FwdSmem {
@@ -323,6 +326,7 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdKernelParams p) {
 
         const f32x2 scale2 = f2_pack(p.sm_scale, p.sm_scale);
         const f32x2 l2e2 = f2_pack(kLog2e, kLog2e);
+        const bool unit_scale = p.sm_scale == 1.0f;
         for (int j = 0; j < num_tiles; ++j) {
             const int col0 = j * kBN;
             float x[kBN];
@@ -356,11 +360,21 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdKernelParams p) {
                     for (int c8 = 0; c8 < 8; ++c8) {
                         const uint4 u = *reinterpret_cast<const uint4*>(brow + ((c8 ^ (r & 7)) << 4));
                         const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+                        if (unit_scale) {
+                            // sm_scale == 1 (T5): S + bias straight from the packed 16-bit pair, one mixed-precision add per element
+                            // (same single rounding as fma(S, 1, bias))
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float2 f = unpack2<kBf16>(w[e]);
-                            const int c = hh * 64 + c8 * 8 + e * 2;
-                            f2_unpack(f2_fma(f2_pack(x[c], x[c + 1]), scale2, f2_pack(f.x, f.y)), x[c], x[c + 1]);   // one FFMA2
+                            for (int e = 0; e < 4; ++e) {
+                                const int c = hh * 64 + c8 * 8 + e * 2;
+                                add_f32_16x2<kBf16>(w[e], x[c], x[c + 1], x[c], x[c + 1]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 f = unpack2<kBf16>(w[e]);
+                                const int c = hh * 64 + c8 * 8 + e * 2;
+                                f2_unpack(f2_fma(f2_pack(x[c], x[c + 1]), scale2, f2_pack(f.x, f.y)), x[c], x[c + 1]);   // one FFMA2
+                            }
                         }
                     }
                     // WAR across proxies: these generic-proxy reads must have completed before the TMA
@@ -423,7 +437,7 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdKernelParams p) {
             }
             const float tmax = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3));
             float alpha = 1.f;
-            if (tmax > m_ref + kRescaleThreshold) {       // also true for the first finite tile (m_ref = -inf)
+            if (tmax > m_ref + kRescaleThreshold<kBf16>) {       // also true for the first finite tile (m_ref = -inf)
                 alpha = __expf(m_ref - tmax);              // exp(-inf) = 0 on the first tile
                 m_ref = tmax;
             }

@@ -47,7 +47,7 @@ def _worker(rank, world, port, tmp):
     qs, ks, vs, dos = (t[a:b] for t in (q, k, v, do))
     o, L = ops.attn_bias_fwd(qs, ks, vs, bias, False, 1.0)
     dq, dk, dv, db32 = ops.attn_bias_bwd_f32dbias(o, dos, qs, ks, vs, bias, L, False, 1.0)
-    grp = comm_group(8)
+    grp = comm_group()
     side = torch.cuda.Stream(device=dev)
     db = allreduce_dbias_f32(db32, torch.bfloat16, side, grp)
     torch.cuda.current_stream().wait_stream(side)
