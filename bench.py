@@ -295,18 +295,16 @@ def run_ours(args):
         sets.append((q, k, v, bias, do))
     F_step = flops_fwd_bwd(B, H, S, S, D)
 
-    def step(i):
+    f32_exchange = world > 1 and args.exchange == "f32"
+
+    def kernels(i):
+        """The attention operators of one step: forward, then backward (dQ, dK, dV, dBias).  Nothing here allocates through the
+        C ABI or synchronises, so the sequence is captured once per input set into a CUDA graph and replayed."""
         q, k, v, bias, do = sets[i % NSETS]
         o, L = torch.ops.b200t5.attn_bias_fwd(q, k, v, bias, False, SM_SCALE)
-        if world > 1 and args.exchange == "f32":
-            # the one exchange of the path: the UNROUNDED fp32 dBias is summed over ranks on a side stream (NCCL capped at a
-            # few CTAs so that it does not take SMs from the attention grids it overlaps) and rounded once afterwards
-            dq, dk, dv, ds32 = torch.ops.b200t5.attn_bias_bwd_f32dbias(o, do, q, k, v, bias, L, False, SM_SCALE)
-            ds = allreduce_dbias_f32(ds32, dtype, comm_stream, dp_group)
-        elif world > 1 and args.exchange == "bf16":       # developer A/B: round first, widen + all-reduce + round again (round 1)
-            dq, dk, dv, ds = torch.ops.b200t5.attn_bias_bwd(o, do, q, k, v, bias, L, False, SM_SCALE)
-            ds = allreduce_dbias_overlapped(ds, comm_stream, dp_group)
-        else:                                               # one rank, or developer A/B --exchange none (INVALID as a DP step)
+        if f32_exchange:
+            dq, dk, dv, ds = torch.ops.b200t5.attn_bias_bwd_f32dbias(o, do, q, k, v, bias, L, False, SM_SCALE)   # unrounded fp32 dBias
+        else:
             dq, dk, dv, ds = torch.ops.b200t5.attn_bias_bwd(o, do, q, k, v, bias, L, False, SM_SCALE)
         return o, dq, dk, dv, ds
 
@@ -319,6 +317,45 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    for i in range(max(args.warmup, 3)):                  # eager warm-up: loads the kernels, sizes the allocator pools
+        kernels(i)
+    barrier()
+
+    # One CUDA graph per input set (forward + the three backward launches): replay removes the host launch path and the
+    # bubbles between dependent launches (~20 us of a 540 us step when launched eagerly from Python).
+    graphs, launches_per_step = None, None
+    if not args.no_graph:
+        graphs = []
+        c0 = _cabi.launch_count()
+        for sidx in range(NSETS):
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                outs = kernels(sidx)
+            graphs.append((gr, outs))
+        launches_per_step = (_cabi.launch_count() - c0) / NSETS
+        torch.cuda.synchronize()
+    buf_free = [None] * NSETS                             # N > 1: the exchange of the step that last used this graph's buffers
+
+    def step(i):
+        sidx = i % NSETS
+        if graphs is not None:
+            if buf_free[sidx] is not None:
+                torch.cuda.current_stream(dev).wait_event(buf_free[sidx])
+            graphs[sidx][0].replay()
+            o, dq, dk, dv, ds = graphs[sidx][1]
+        else:
+            o, dq, dk, dv, ds = kernels(i)
+        if world > 1 and args.exchange == "f32":
+            # the one exchange of the path: the UNROUNDED fp32 dBias is summed over ranks on a side stream (NCCL capped at a
+            # few CTAs so that it does not take SMs from the attention grids it overlaps) and rounded once afterwards
+            ds = allreduce_dbias_f32(ds, dtype, comm_stream, dp_group)
+        elif world > 1 and args.exchange == "bf16":       # developer A/B: round first, widen + all-reduce + round again (round 1)
+            ds = allreduce_dbias_overlapped(ds, comm_stream, dp_group)
+        if world > 1 and graphs is not None and args.exchange != "none":
+            buf_free[sidx] = torch.cuda.Event()
+            buf_free[sidx].record(comm_stream)
+        return o, dq, dk, dv, ds
+
     for i in range(max(args.warmup, 3)):
         step(i)
     barrier()
@@ -326,8 +363,9 @@ def run_ours(args):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    _cabi.profile_enable(True)
-    _cabi.profile_collect()
+    if graphs is None:
+        _cabi.profile_enable(True)                          # per-kernel CUDA-event pairs inside the library (eager launches only)
+        _cabi.profile_collect()
     launches0 = _cabi.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -339,9 +377,24 @@ def run_ours(args):
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
-    launches = _cabi.launch_count() - launches0
-    prof = _cabi.profile_collect()
-    _cabi.profile_enable(False)
+    if graphs is None:
+        launches = _cabi.launch_count() - launches0
+        prof = _cabi.profile_collect()
+        _cabi.profile_enable(False)
+        prof_note = "CUDA-event pairs around every launch of the timed region"
+    else:
+        launches = launches_per_step * args.steps          # kernel nodes replayed: counted when the graphs were captured
+        # A replayed graph cannot carry event pairs: the per-kernel durations of the roofline come from an eager pass of the
+        # same steps right after the timed region (same inputs, same clocks; clock sampler still running).
+        n_prof = min(args.steps, 40)
+        _cabi.profile_enable(True)
+        _cabi.profile_collect()
+        for i in range(n_prof):
+            kernels(i)
+        torch.cuda.synchronize()
+        prof = _cabi.profile_collect()
+        _cabi.profile_enable(False)
+        prof_note = "CUDA-event pairs around every launch of %d eager steps run right after the timed (graph-replayed) region" % n_prof
     clocks = sampler.stop() if sampler else None
 
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
@@ -359,9 +412,9 @@ def run_ours(args):
     if bwd_ms:
         avg = sum(bwd_ms) / len(bwd_ms)
         ach = 2.5 * flops_fwd(B, H, S, S, D) / (avg * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "kernel": "attn_bwd_kernel (fused dQ/dK/dV/dS)", "achieved": ach, "peak": peak,
+        roofline = {"bound": "tensor", "kernel": "attn_bwd_kernel_v3 (fused S^T/dP^T/dV/dK/dQ + dS^T out)", "achieved": ach, "peak": peak,
                     "unit": "TFLOP/s", "frac": ach / peak, "traffic": load_traffic(), "peak_source": peak_src,
-                    "avg_launch_ms": avg, "launches_timed": len(bwd_ms),
+                    "avg_launch_ms": avg, "launches_timed": len(bwd_ms), "timing": prof_note,
                     "algorithmic_flops_per_launch": 2.5 * flops_fwd(B, H, S, S, D)}
         if fwd_ms:
             favg = sum(fwd_ms) / len(fwd_ms)
@@ -500,11 +553,25 @@ def run_ours(args):
             for i in range(3):
                 rpe_step(i)
             torch.cuda.synchronize()
+            rpe_graphs = None
+            if not args.no_graph:                              # same launch mode as the headline loop
+                rpe_graphs = []
+                for sidx in range(NSETS):
+                    gr = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gr):
+                        keep = rpe_step(sidx)
+                    rpe_graphs.append((gr, keep))
+                for gr, _ in rpe_graphs:
+                    gr.replay()
+                torch.cuda.synchronize()
             n_rpe = max(3, min(args.steps, 50))
             r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             r0.record()
             for i in range(n_rpe):
-                rpe_step(i)
+                if rpe_graphs is not None:
+                    rpe_graphs[i % NSETS][0].replay()
+                else:
+                    rpe_step(i)
             r1.record()
             torch.cuda.synchronize()
             rms = r0.elapsed_time(r1) / n_rpe
@@ -528,6 +595,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": WB * world, "seq_len": WS, "parallelism": "dp%d" % world,
                        "l2": "inputs rotate over %d buffer sets of 185 MB each (> 126 MB L2)" % NSETS,
+                       "launch": "eager" if args.no_graph else "one CUDA graph per input set (fwd + 3 backward launches), replayed",
                        "exchange": ("none" if world == 1 else
                                     "DEVELOPER A/B --exchange %s --nccl-ctas %d: not the product configuration" % (args.exchange, args.nccl_ctas)
                                     if (args.exchange != "f32" or args.nccl_ctas != 16) else
@@ -556,6 +624,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sustained", action="store_true")
     ap.add_argument("--no-siblings", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying the captured CUDA graphs")
     ap.add_argument("--exchange", default="f32", choices=["f32", "bf16", "none"], help="developer A/B of the N > 1 dBias exchange (the product is f32)")
     ap.add_argument("--nccl-ctas", type=int, default=16, help="CTA cap of the exchange communicator (0: NCCL's default group)")
     args = ap.parse_args()

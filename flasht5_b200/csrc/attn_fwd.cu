@@ -377,12 +377,15 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdKernelParams p) {
                             }
                         }
                     }
-                    // WAR across proxies: these generic-proxy reads must have completed before the TMA
-                    // (async proxy) may overwrite the stage.  Without the fence ~0.1% of rows picked up
-                    // bytes of the NEXT tile when two CTAs shared an SM (measured on B200).
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bars.b_empty + s);
+                }
+                // WAR across proxies: these generic-proxy reads must have completed before the TMA (async proxy) may
+                // overwrite the stages.  Without the fence ~0.1% of rows picked up bytes of the NEXT tile when two CTAs
+                // shared an SM (measured on B200).  One fence for both halves of the tile: it costs ~100 cycles of latency.
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(bars.b_empty + (2 * j) % kBiasStages);
+                    mbar_arrive(bars.b_empty + (2 * j + 1) % kBiasStages);
                 }
             } else if (kBiasMode == 2) {
 #pragma unroll
