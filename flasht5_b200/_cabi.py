@@ -70,6 +70,7 @@ class AdamwTensor(C.Structure):
 _i64, _i32, _f, _vp, _sz = C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_size_t
 SYMBOLS = {
     "b200t5_attn_fwd": (_i32, [C.POINTER(AttnParams)]),
+    "b200t5_attn_fwd_workspace_bytes": (_sz, [C.POINTER(AttnParams)]),
     "b200t5_attn_bwd_workspace_bytes": (_sz, [C.POINTER(AttnParams)]),
     "b200t5_attn_bwd": (_i32, [C.POINTER(AttnParams)]),
     "b200t5_rmsnorm_fwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _f, _i32, _i32, _i32, _vp]),

@@ -208,6 +208,11 @@ static int bias_mode_of(const b200t5_attn_params* p) {
 }
 
 static int round_up8(int x) { return (x + 7) / 8 * 8; }
+// forward workspace: only for a bias whose rows a tensor map cannot address (the aligned copy)
+static size_t fwd_workspace_bytes(const b200t5_attn_params* p) {
+    if (bias_mode_of(p) != 2) return 0;
+    return ((size_t)p->bias_B * p->bias_H * p->M * (size_t)round_up8(p->N) * 2 + 255) / 256 * 256;
+}
 static int check_dtype3(int dt, const char* what) {
     if (dt == B200T5_F16 || dt == B200T5_BF16 || dt == B200T5_F32) return 0;
     return fail(B200T5_ERR_UNSUPPORTED, "%s dtype %d not in {fp16, bf16, fp32}", what, dt);
@@ -272,8 +277,16 @@ static int attn_fwd_impl(const b200t5_attn_params* p, const b200t5_rpe_params* r
     if ((rc = make_map_4d(&kp.map_q, p->q, 2, dt, p->D, p->M, p->H, p->B, p->q_strides[2], p->q_strides[1], p->q_strides[0], boxd, 128, "q"))) return rc;
     if ((rc = make_map_4d(&kp.map_k, p->k, 2, dt, p->D, p->N, p->H, p->B, p->k_strides[2], p->k_strides[1], p->k_strides[0], boxd, 128, "k"))) return rc;
     if ((rc = make_map_4d(&kp.map_v, p->v, 2, dt, p->D, p->N, p->H, p->B, p->v_strides[2], p->v_strides[1], p->v_strides[0], boxd, 128, "v"))) return rc;
-    const int mode = rpe ? 3 : bias_mode_of(p);
-    if (mode == 1) {
+    int mode = rpe ? 3 : bias_mode_of(p);
+    if (mode == 2 && p->workspace && p->workspace_bytes >= fwd_workspace_bytes(p) && reinterpret_cast<uintptr_t>(p->workspace) % 256 == 0) {
+        // rows a tensor map cannot address: aligned copy in the caller's workspace, then the TMA path
+        const int pitch = round_up8(p->N);
+        cudaError_t ce = launch_bias_align_copy(p->bias, p->bias_strides, p->workspace, p->bias_B, p->bias_H, p->M, p->N, pitch,
+                                                static_cast<cudaStream_t>(p->stream));
+        if (ce != cudaSuccess) return fail_cuda(ce, "bias_align_copy launch");
+        if ((rc = make_map_4d(&kp.map_bias, p->workspace, 2, dt, p->N, p->M, p->bias_H, p->bias_B, pitch, (int64_t)p->M * pitch, (int64_t)p->bias_H * p->M * pitch, 64, 128, "bias (aligned copy)"))) return rc;
+        mode = 1;
+    } else if (mode == 1) {
         if ((rc = make_map_4d(&kp.map_bias, p->bias, 2, dt, p->N, p->M, p->bias_H, p->bias_B, p->bias_strides[2], p->bias_strides[1], p->bias_strides[0], 64, 128, "bias"))) return rc;
     } else if (mode == 2) {
         kp.bias = p->bias;
@@ -306,6 +319,10 @@ static int attn_fwd_impl(const b200t5_attn_params* p, const b200t5_rpe_params* r
 }
 
 extern "C" int b200t5_attn_fwd(const b200t5_attn_params* p) { return attn_fwd_impl(p, nullptr); }
+extern "C" size_t b200t5_attn_fwd_workspace_bytes(const b200t5_attn_params* p) {
+    if (!p || p->B < 1 || p->H < 1 || p->M < 1 || p->N < 1 || p->D < 1 || !p->bias) return 0;
+    return fwd_workspace_bytes(p);
+}
 extern "C" int b200t5_attn_rpe_fwd(const b200t5_attn_params* p, const b200t5_rpe_params* r) {
     if (!r) return fail(B200T5_ERR_INVALID, "rpe params is NULL");
     return attn_fwd_impl(p, r);
@@ -361,7 +378,9 @@ BwdWorkspace bwd_workspace_layout(const b200t5_attn_params* p, bool has_rpe = fa
     w.ds_bytes = ds_bytes;
     w.bias_t_off = w.ds_off + align(ds_bytes);
     // repacked dense bias of the v3 kernel: [bias_B][bias_H][key blocks of 128][query blocks of 32][4][128][8] 16-bit
-    const size_t bias_t_bytes = (w.transposed && p->bias) ? (size_t)p->bias_B * p->bias_H * (size_t)((p->N + 127) / 128) * (size_t)(4 * ((p->M + 127) / 128)) * 4 * 128 * 16 : 0;   // whole 128-query tiles: the kernel reads every sub-tile of its last tile
+    size_t bias_t_bytes = (w.transposed && p->bias) ? (size_t)p->bias_B * p->bias_H * (size_t)((p->N + 127) / 128) * (size_t)(4 * ((p->M + 127) / 128)) * 4 * 128 * 16 : 0;   // whole 128-query tiles: the kernel reads every sub-tile of its last tile
+    // D = 128 with bias rows a tensor map cannot address: the same region holds the aligned copy (rows padded to 8 elements)
+    if (!w.transposed && p->bias && bias_mode_of(p) == 2) bias_t_bytes = fwd_workspace_bytes(p);
     w.dbias_off = w.bias_t_off + align(bias_t_bytes);
     const bool dense_scratch = has_rpe && !(w.transposed && rpe_skip && rpe_skip_const_level() >= 2);
     w.dconst_off = w.dbias_off + (dense_scratch ? align((size_t)p->H * p->M * (size_t)p->N * 2) : 0);
@@ -439,7 +458,7 @@ static int attn_bwd_impl(const b200t5_attn_params* p, const b200t5_rpe_params* r
     if ((rc = make_map_4d(&kp.map_dq, dq_ws, 2, dt, p->D, p->M, p->H, (uint64_t)w.dq_groups * p->B, p->D, (int64_t)p->M * p->D, (int64_t)p->H * p->M * p->D, boxd, 128, "dq group surface", true))) return rc;
     kp.dq_groups = w.dq_groups;
     // D <= 64: every dense bias goes through the transposed copy (which also absorbs unaligned rows); D = 128: TMA or pointers
-    const int mode = rpe ? 3 : (p->bias ? (w.transposed ? 1 : bias_mode_of(p)) : 0);
+    int mode = rpe ? 3 : (p->bias ? (w.transposed ? 1 : bias_mode_of(p)) : 0);
     float* dconst = nullptr;
     if (mode == 3) {
         fill_rpe_band(&kp.rpe, rpe);
@@ -458,14 +477,15 @@ static int attn_bwd_impl(const b200t5_attn_params* p, const b200t5_rpe_params* r
         kp.k = p->k; kp.k_sb = p->k_strides[0]; kp.k_sh = p->k_strides[1]; kp.k_sn = p->k_strides[2];
         kp.v = p->v; kp.v_sb = p->v_strides[0]; kp.v_sh = p->v_strides[1]; kp.v_sn = p->v_strides[2];
     } else {
-        if (mode == 1) {
+        if (mode == 2) {
+            // unaligned bias rows: aligned copy in the workspace, then the TMA path (as in the forward)
+            const int pitch = round_up8(p->N);
+            e = launch_bias_align_copy(p->bias, p->bias_strides, ws + w.bias_t_off, p->bias_B, p->bias_H, p->M, p->N, pitch, stream);
+            if (e != cudaSuccess) return fail_cuda(e, "bias_align_copy launch");
+            if ((rc = make_map_4d(&kp.map_bias, ws + w.bias_t_off, 2, dt, p->N, p->M, p->bias_H, p->bias_B, pitch, (int64_t)p->M * pitch, (int64_t)p->bias_H * p->M * pitch, 64, 128, "bias (aligned copy)"))) return rc;
+            mode = 1;
+        } else if (mode == 1) {
             if ((rc = make_map_4d(&kp.map_bias, p->bias, 2, dt, p->N, p->M, p->bias_H, p->bias_B, p->bias_strides[2], p->bias_strides[1], p->bias_strides[0], 64, 128, "bias"))) return rc;
-        } else if (mode == 2) {
-            kp.bias = p->bias;
-            kp.bias_sb = p->bias_strides[0];
-            kp.bias_sh = p->bias_strides[1];
-            kp.bias_sm = p->bias_strides[2];
-            kp.bias_sn = p->bias_strides[3];
         }
         if (mode != 0) {
             // dS tiles always go to the (B, H, M, n_pad) 16-bit workspace through TMA stores

@@ -1032,11 +1032,13 @@ __global__ void __launch_bounds__(256) attn_bwd_post_fused_kernel(const uint4* _
                                                                   void* __restrict__ dbias, int64_t o_sb, int64_t o_sh, int64_t o_sm,
                                                                   int64_t o_sn, int G, int N, int reduce_b, int reduce_h, int causal, int gx,
                                                                   int gy) {
-    if (static_cast<int>(blockIdx.x) < cvt_blocks) {
-        attn_bwd_dq_convert_body<kD, kBf16>(dq_ws, dq_groups, dq, sb, sh, sm, B, H, M, scale, blockIdx.x);
+    // the (heavier) reduction blocks come first: the light conversion blocks fill the tail of the grid
+    const int red_blocks = static_cast<int>(gridDim.x) - cvt_blocks;
+    if (static_cast<int>(blockIdx.x) >= red_blocks) {
+        attn_bwd_dq_convert_body<kD, kBf16>(dq_ws, dq_groups, dq, sb, sh, sm, B, H, M, scale, static_cast<int>(blockIdx.x) - red_blocks);
         return;
     }
-    const int id = static_cast<int>(blockIdx.x) - cvt_blocks;
+    const int id = static_cast<int>(blockIdx.x);
     dbias_reduce_t_body<kBf16, kOutF32>(ws, m_pitch, dbias, o_sb, o_sh, o_sm, o_sn, G, H, M, N, reduce_b, reduce_h, causal, id % gx,
                                         (id / gx) % gy, id / (gx * gy));
 }

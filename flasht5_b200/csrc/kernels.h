@@ -81,6 +81,8 @@ struct AttnBwdKernelParams {
     RpeBand rpe;
 };
 
+cudaError_t launch_bias_align_copy(const void* bias, const int64_t* strides, void* dst, int Bb, int Hb, int M, int N, int pitch,
+                                   cudaStream_t stream);
 cudaError_t launch_attn_fwd(const AttnFwdKernelParams& kp, int D, bool bf16, int bias_mode, bool causal,
                             cudaStream_t stream);
 cudaError_t launch_attn_bwd(const AttnBwdKernelParams& kp, int D, bool bf16, int bias_mode, bool causal,

@@ -110,6 +110,10 @@ def attn_bias_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, bias: Optio
     p = _base_params(q, k, v, bias, causal, sm_scale)
     p.o, p.o_strides = o.data_ptr(), _cabi.strides4(o)
     p.lse = L.data_ptr()
+    nbytes = lib.b200t5_attn_fwd_workspace_bytes(C.byref(p))        # > 0 only for bias rows a tensor map cannot address
+    if nbytes:
+        ws = torch.empty(nbytes, device=q.device, dtype=torch.uint8)
+        p.workspace, p.workspace_bytes = ws.data_ptr(), nbytes
     _cabi.check(lib.b200t5_attn_fwd(C.byref(p)), "b200t5_attn_fwd")
     return o, L
 

@@ -97,6 +97,11 @@ typedef struct b200t5_attn_params {
 } b200t5_attn_params;
 
 B200T5_API int b200t5_attn_fwd(const b200t5_attn_params* p);
+/* Optional forward workspace: non-zero only for a bias whose rows a TMA tensor map cannot address (N % 8 != 0, a row stride
+ * that is not a multiple of 8 elements, an unaligned base).  Given >= this many bytes in p->workspace (256-B aligned) the
+ * forward copies the bias once into rows padded to 8 elements and streams it with TMA; without it the bias is read
+ * element by element (correct, ~2x slower forward).  The reference has no such restriction to mirror (Triton pointers). */
+B200T5_API size_t b200t5_attn_fwd_workspace_bytes(const b200t5_attn_params* p);
 B200T5_API size_t b200t5_attn_bwd_workspace_bytes(const b200t5_attn_params* p);
 B200T5_API int b200t5_attn_bwd(const b200t5_attn_params* p);
 
