@@ -8,7 +8,7 @@ reference's own Python operator surface on top.
 The layout follows the reference's src/model/ops/: one module per operator, same function and
 class names, same argument meaning.  No Triton, no multi-backend dispatch, no CPU fallback.
 """
-from .flash_attention_v2_bias import FlashAttentionAdditiveBias, flash_attention_v2_bias
+from .flash_attention_v2_bias import FlashAttentionAdditiveBias, SharedBiasGrad, flash_attention_v2_bias, flash_attention_v2_bias_shared
 from .rms_norm import Fast_RMS_Layernorm, fast_rms_layernorm
 from .cross_entropy_loss import CrossEntropyLoss, cross_entropy_loss
 from .positional_encoding import RelativePositionalEncoding
@@ -16,7 +16,7 @@ from .flash_attention_rpe import FlashAttentionRPE, flash_attention_v2_rpe
 from .adamw_scaled import AdamWScale
 
 __all__ = [
-    "flash_attention_v2_bias", "FlashAttentionAdditiveBias",
+    "flash_attention_v2_bias", "FlashAttentionAdditiveBias", "flash_attention_v2_bias_shared", "SharedBiasGrad",
     "fast_rms_layernorm", "Fast_RMS_Layernorm",
     "cross_entropy_loss", "CrossEntropyLoss",
     "RelativePositionalEncoding",

@@ -22,6 +22,7 @@ I64x4 = C.c_int64 * 4
 
 ATTN_DETERMINISTIC = 1      # b200t5_attn_params.flags (include/b200t5.h)
 ATTN_DBIAS_F32 = 2
+ATTN_DBIAS_ACCUMULATE = 4
 
 
 class AttnParams(C.Structure):

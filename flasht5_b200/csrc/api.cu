@@ -413,6 +413,7 @@ static int attn_bwd_impl(const b200t5_attn_params* p, const b200t5_rpe_params* r
     if (!strides_tma_ok(p->dout, p->do_strides, p->B, p->H) || !strides_tma_ok(p->dq, p->dq_strides, p->B, p->H) ||
         !strides_tma_ok(p->dk, p->dk_strides, p->B, p->H) || !strides_tma_ok(p->dv, p->dv_strides, p->B, p->H))
         return fail(B200T5_ERR_INVALID, "dout, dq, dk, dv need unit last stride, 16-byte aligned base and other strides that are multiples of 8 elements");
+    if ((p->flags & B200T5_ATTN_DBIAS_ACCUMULATE) && !(p->flags & B200T5_ATTN_DBIAS_F32)) return fail(B200T5_ERR_INVALID, "B200T5_ATTN_DBIAS_ACCUMULATE needs B200T5_ATTN_DBIAS_F32 (the accumulator is an fp32 tensor)");
     if ((p->flags & B200T5_ATTN_DBIAS_F32) && (p->D > 64 || rpe)) return fail(B200T5_ERR_UNSUPPORTED, "B200T5_ATTN_DBIAS_F32 is implemented for head dims 16 / 32 / 64 of the dense-bias operator");
     const bool rpe_skip = rpe != nullptr && rpe_skip_const_enabled() && p->D <= 64;   // the D = 128 kernel stores every tile
     const BwdWorkspace w = bwd_workspace_layout(p, rpe != nullptr, rpe_skip);
@@ -533,7 +534,8 @@ static int attn_bwd_impl(const b200t5_attn_params* p, const b200t5_rpe_params* r
     if (w.transposed) {
         e = launch_attn_bwd_post_fused(dq_ws, w.dq_groups, p->dq, p->dq_strides, p->B, p->H, p->M, p->N, p->D, p->sm_scale, bf16, ds_ws,
                                        w.ds_pitch, dbias_out, dbias_strides, G, reduce_b, reduce_h, causal,
-                                       !rpe && (p->flags & B200T5_ATTN_DBIAS_F32) != 0, stream);
+                                       !rpe && (p->flags & B200T5_ATTN_DBIAS_F32) != 0, stream,
+                                       !rpe && (p->flags & B200T5_ATTN_DBIAS_ACCUMULATE) != 0);
         if (e != cudaSuccess) return fail_cuda(e, "attn_bwd finalize launch");
     } else {
         e = launch_attn_bwd_finalize(dq_ws, w.dq_groups, p->dq, p->dq_strides, p->B, p->H, p->M, p->N, p->D, p->sm_scale, bf16,

@@ -938,7 +938,8 @@ cudaError_t launch_bias_repack(const void* bias, const int64_t* s, void* bias_p,
 template <bool kBf16, bool kOutF32>
 __device__ __forceinline__ void dbias_reduce_t_body(const uint16_t* __restrict__ ws, int m_pitch, void* __restrict__ out_v,
                                                     int64_t o_sb, int64_t o_sh, int64_t o_sm, int64_t o_sn, int G, int H,
-                                                    int M, int N, int reduce_b, int reduce_h, int causal, int bx, int by, int bz) {
+                                                    int M, int N, int reduce_b, int reduce_h, int causal, int bx, int by, int bz,
+                                                    bool accumulate = false) {
     // thread (ty, tx) = (tid / 8, tid % 8): loads 16 bytes = 8 consecutive m of rows n0 + ty and n0 + ty + 32 (a warp reads
     // four 128-byte row segments per instruction), writes 8 consecutive n of rows m0 + ty and m0 + ty + 32 the same way.
     __shared__ float tile[64][65];
@@ -948,6 +949,8 @@ __device__ __forceinline__ void dbias_reduce_t_body(const uint16_t* __restrict__
     const int ty = threadIdx.x >> 3, tx = threadIdx.x & 7;
     const int pseq = N - M;
     const bool tile_masked = causal && (n0 > m0 + 63 + pseq);              // every (m, n) of the tile is above the diagonal
+    // accumulate (fp32 output only): out += sum -- a tile that is entirely masked adds nothing
+    if (kOutF32 && accumulate && tile_masked) return;
     float acc[2][8];
 #pragma unroll
     for (int j = 0; j < 2; ++j)
@@ -999,6 +1002,11 @@ __device__ __forceinline__ void dbias_reduce_t_body(const uint16_t* __restrict__
         if (vec_ok && nb + 8 <= N) {
             if constexpr (kOutF32) {
                 float4* dst = reinterpret_cast<float4*>(static_cast<float*>(out_v) + oi);
+                if (accumulate) {
+                    const float4 a0 = dst[0], a1 = dst[1];
+                    v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
+                    v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
+                }
                 dst[0] = make_float4(v[0], v[1], v[2], v[3]);
                 dst[1] = make_float4(v[4], v[5], v[6], v[7]);
             } else {
@@ -1009,7 +1017,7 @@ __device__ __forceinline__ void dbias_reduce_t_body(const uint16_t* __restrict__
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 if (nb + e >= N) continue;
-                if constexpr (kOutF32) static_cast<float*>(out_v)[oi + e * o_sn] = v[e];
+                if constexpr (kOutF32) static_cast<float*>(out_v)[oi + e * o_sn] = accumulate ? static_cast<float*>(out_v)[oi + e * o_sn] + v[e] : v[e];
                 else static_cast<uint16_t*>(out_v)[oi + e * o_sn] = static_cast<uint16_t>(pack2<kBf16>(v[e], 0.f) & 0xFFFFu);
             }
         }
@@ -1019,9 +1027,9 @@ __device__ __forceinline__ void dbias_reduce_t_body(const uint16_t* __restrict__
 template <bool kBf16, bool kOutF32>
 __global__ void __launch_bounds__(256) dbias_reduce_t_kernel(const uint16_t* __restrict__ ws, int m_pitch, void* __restrict__ out_v,
                                                              int64_t o_sb, int64_t o_sh, int64_t o_sm, int64_t o_sn, int G, int H,
-                                                             int M, int N, int reduce_b, int reduce_h, int causal) {
+                                                             int M, int N, int reduce_b, int reduce_h, int causal, int accumulate) {
     dbias_reduce_t_body<kBf16, kOutF32>(ws, m_pitch, out_v, o_sb, o_sh, o_sm, o_sn, G, H, M, N, reduce_b, reduce_h, causal, blockIdx.x,
-                                        blockIdx.y, blockIdx.z);
+                                        blockIdx.y, blockIdx.z, accumulate != 0);
 }
 
 // dQ conversion and the transposing dBias reduction in ONE launch (independent work; block-index split)
@@ -1031,7 +1039,7 @@ __global__ void __launch_bounds__(256) attn_bwd_post_fused_kernel(const uint4* _
                                                                   int cvt_blocks, const uint16_t* __restrict__ ws, int m_pitch,
                                                                   void* __restrict__ dbias, int64_t o_sb, int64_t o_sh, int64_t o_sm,
                                                                   int64_t o_sn, int G, int N, int reduce_b, int reduce_h, int causal, int gx,
-                                                                  int gy) {
+                                                                  int gy, int accumulate) {
     // the (heavier) reduction blocks come first: the light conversion blocks fill the tail of the grid
     const int red_blocks = static_cast<int>(gridDim.x) - cvt_blocks;
     if (static_cast<int>(blockIdx.x) >= red_blocks) {
@@ -1040,17 +1048,17 @@ __global__ void __launch_bounds__(256) attn_bwd_post_fused_kernel(const uint4* _
     }
     const int id = static_cast<int>(blockIdx.x);
     dbias_reduce_t_body<kBf16, kOutF32>(ws, m_pitch, dbias, o_sb, o_sh, o_sm, o_sn, G, H, M, N, reduce_b, reduce_h, causal, id % gx,
-                                        (id / gx) % gy, id / (gx * gy));
+                                        (id / gx) % gy, id / (gx * gy), accumulate != 0);
 }
 
 cudaError_t launch_dbias_reduce_t(const void* ds_t, int m_pitch, void* dbias, const int64_t* s, int G, int H, int M, int N,
-                                  int reduce_b, int reduce_h, bool causal, bool bf16, bool out_f32, cudaStream_t stream) {
+                                  int reduce_b, int reduce_h, bool causal, bool bf16, bool out_f32, cudaStream_t stream, bool accumulate) {
     const int ob = reduce_b ? 1 : G, oh = reduce_h ? 1 : H;
     const dim3 grid((M + 63) / 64, (N + 63) / 64, ob * oh);
     if (grid.y > 65535 || grid.z > 65535) return cudaErrorInvalidValue;
 #define B200T5_DBR(BF, F32)                                                                                                   \
     dbias_reduce_t_kernel<BF, F32><<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(ds_t), m_pitch, dbias, s[0], s[1], s[2], \
-                                                             s[3], G, H, M, N, reduce_b, reduce_h, causal ? 1 : 0)
+                                                             s[3], G, H, M, N, reduce_b, reduce_h, causal ? 1 : 0, accumulate ? 1 : 0)
     if (bf16) { if (out_f32) B200T5_DBR(true, true); else B200T5_DBR(true, false); }
     else { if (out_f32) B200T5_DBR(false, true); else B200T5_DBR(false, false); }
 #undef B200T5_DBR
@@ -1214,7 +1222,7 @@ cudaError_t launch_attn_bwd_pre_fused(const void* o, const int64_t* os, const vo
 cudaError_t launch_attn_bwd_post_fused(const void* dq_ws, int dq_groups, void* dq, const int64_t* dqs, int B, int H, int M, int N,
                                        int D, float sm_scale, bool bf16, const void* ds_t, int m_pitch, void* dbias,
                                        const int64_t* dbs, int G, int reduce_b, int reduce_h, bool causal, bool out_f32,
-                                       cudaStream_t stream) {
+                                       cudaStream_t stream, bool accumulate) {
     if (dbias == nullptr) return launch_attn_bwd_dq_convert(dq_ws, dq_groups, dq, dqs, B, H, M, D, sm_scale, bf16, stream);
     const int64_t cvt_threads = (int64_t)B * H * M * (D / 8);
     const int cvt_blocks = static_cast<int>((cvt_threads + 255) / 256);
@@ -1227,7 +1235,7 @@ cudaError_t launch_attn_bwd_post_fused(const void* dq_ws, int dq_groups, void* d
     attn_bwd_post_fused_kernel<DD, BF, F32><<<grid, 256, 0, stream>>>(                                                          \
         static_cast<const uint4*>(dq_ws), dq_groups, static_cast<uint8_t*>(dq), dqs[0], dqs[1], dqs[2], B, H, M, sm_scale,      \
         cvt_blocks, static_cast<const uint16_t*>(ds_t), m_pitch, dbias, dbs[0], dbs[1], dbs[2], dbs[3], G, N, reduce_b, reduce_h, \
-        causal ? 1 : 0, gx, gy)
+        causal ? 1 : 0, gx, gy, accumulate ? 1 : 0)
 #define B200T5_POSTF2(DD)                                                                            \
     if (bf16) { if (out_f32) B200T5_POSTF(DD, true, true); else B200T5_POSTF(DD, true, false); }     \
     else { if (out_f32) B200T5_POSTF(DD, false, true); else B200T5_POSTF(DD, false, false); }

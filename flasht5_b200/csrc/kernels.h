@@ -105,13 +105,13 @@ cudaError_t launch_attn_bwd_pre_fused(const void* o, const int64_t* o_strides, c
 cudaError_t launch_attn_bwd_post_fused(const void* dq_ws, int dq_groups, void* dq, const int64_t* dq_strides, int B, int H, int M,
                                        int N, int D, float sm_scale, bool bf16, const void* ds_t, int m_pitch, void* dbias,
                                        const int64_t* dbias_strides, int G, int reduce_b, int reduce_h, bool causal, bool out_f32,
-                                       cudaStream_t stream);
+                                       cudaStream_t stream, bool accumulate = false);
 // dbias[bb,hb,m,n] = sum over broadcast batch-group / head of ds_t[g,h,n,m] (the transposed surface of the v3 kernel);
 // fp32 accumulation, one rounding; causal-masked entries are written as 0 without being read
-// out_f32: dbias is an fp32 tensor (unrounded sums) instead of the io dtype
+// out_f32: dbias is an fp32 tensor (unrounded sums) instead of the io dtype; accumulate (fp32 only): dbias += the sums
 cudaError_t launch_dbias_reduce_t(const void* ds_t, int m_pitch, void* dbias, const int64_t* dbias_strides, int G, int H,
                                   int M, int N, int reduce_b, int reduce_h, bool causal, bool bf16, bool out_f32,
-                                  cudaStream_t stream);
+                                  cudaStream_t stream, bool accumulate = false);
 
 // delta[b,h,m] = sum_d O*dO  (fp32); also zero-fills the 16-bit dQ group surface (dq_groups, B, H, M, D).
 // `zero_ptr` / `zero_bytes` (multiple of 16, may be 0): an extra surface to zero-fill in the same launch.

@@ -36,7 +36,8 @@ import torch
 
 from . import _cabi
 
-__all__ = ["flash_attention_v2_bias", "FlashAttentionAdditiveBias", "attn_bias_fwd", "attn_bias_bwd", "attn_bias_bwd_f32dbias"]
+__all__ = ["flash_attention_v2_bias", "FlashAttentionAdditiveBias", "attn_bias_fwd", "attn_bias_bwd", "attn_bias_bwd_f32dbias",
+           "attn_bias_bwd_accum", "SharedBiasGrad", "flash_attention_v2_bias_shared"]
 
 
 def _aligned(t: torch.Tensor) -> bool:
@@ -188,6 +189,42 @@ def _attn_bias_bwd_f32dbias_fake(o, do, q, k, v, bias, L, causal, sm_scale):
     return torch.empty_like(q), torch.empty_like(k), torch.empty_like(v), torch.empty(bias.shape, dtype=torch.float32, device=q.device)
 
 
+@torch.library.custom_op("b200t5::attn_bias_bwd_accum", mutates_args=("dbias_acc",), device_types="cuda")
+def attn_bias_bwd_accum(o: torch.Tensor, do: torch.Tensor, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor,
+                        bias: torch.Tensor, L: torch.Tensor, dbias_acc: torch.Tensor, causal: bool,
+                        sm_scale: float) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """(dq, dk, dv); the batch-summed dS is ADDED, unrounded, into the fp32 tensor `dbias_acc` of bias's shape (C ABI flags
+    B200T5_ATTN_DBIAS_F32 | B200T5_ATTN_DBIAS_ACCUMULATE; head dims 16 / 32 / 64).  SURVEY.md section 8 row f2: the layers of a
+    stack share one bias (reference modeling_flash_t5.py:452-455) and accumulate its gradient here instead of in autograd."""
+    _cabi.require_cuda(o, do, q, k, v, bias, L, dbias_acc)
+    B, H, M, N, D = _check_shapes(q, k, v, bias)
+    if dbias_acc.dtype != torch.float32 or dbias_acc.shape != bias.shape:
+        raise ValueError("dbias_acc must be an fp32 tensor of bias's shape")
+    lib = _cabi.load()
+    q, k, v, o, do = _prep(q), _prep(k), _prep(v), _prep(o), _prep(do)
+    L = L.contiguous()
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    p = _base_params(q, k, v, bias, causal, sm_scale)
+    p.flags |= _cabi.ATTN_DBIAS_F32 | _cabi.ATTN_DBIAS_ACCUMULATE
+    p.o, p.o_strides = o.data_ptr(), _cabi.strides4(o)
+    p.lse = L.data_ptr()
+    p.dout, p.do_strides = do.data_ptr(), _cabi.strides4(do)
+    p.dq, p.dq_strides = dq.data_ptr(), _cabi.strides4(dq)
+    p.dk, p.dk_strides = dk.data_ptr(), _cabi.strides4(dk)
+    p.dv, p.dv_strides = dv.data_ptr(), _cabi.strides4(dv)
+    p.dbias, p.dbias_strides = dbias_acc.data_ptr(), _cabi.strides4(dbias_acc)
+    nbytes = lib.b200t5_attn_bwd_workspace_bytes(C.byref(p))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=q.device)
+    p.workspace, p.workspace_bytes = ws.data_ptr(), nbytes
+    _cabi.check(lib.b200t5_attn_bwd(C.byref(p)), "b200t5_attn_bwd")
+    return dq, dk, dv
+
+
+@torch.library.register_fake("b200t5::attn_bias_bwd_accum")
+def _attn_bias_bwd_accum_fake(o, do, q, k, v, bias, L, dbias_acc, causal, sm_scale):
+    return torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+
+
 @torch.library.register_fake("b200t5::attn_bias_bwd")
 def _attn_bias_bwd_fake(o, do, q, k, v, bias, L, causal, sm_scale):
     ds = torch.empty_like(bias, memory_format=torch.contiguous_format) if bias is not None \
@@ -216,6 +253,58 @@ class FlashAttentionAdditiveBias(torch.autograd.Function):
         q, k, v, bias, o, L = ctx.saved_tensors
         dq, dk, dv, ds = torch.ops.b200t5.attn_bias_bwd(o, do, q, k, v, bias, L, ctx.causal, ctx.sm_scale)
         return dq, dk, dv, (ds if bias is not None else None), None, None
+
+
+class SharedBiasGrad:
+    """Gradient accumulator of ONE bias tensor shared by several attention layers.
+
+    The reference computes the position bias once per stack and hands the same tensor to every layer
+    (modeling_flash_t5.py:437-457), so autograd adds L dense (1, H, M, N) gradients per stack, each already rounded to 16
+    bits.  With one `SharedBiasGrad()` per (stack, step) passed to `flash_attention_v2_bias_shared`, every layer's backward
+    adds its unrounded batch-summed dS into one persistent fp32 buffer inside the finalize kernel, and autograd receives a
+    single gradient -- from the layer whose backward runs last -- rounded once."""
+
+    def __init__(self):
+        self.buf: Optional[torch.Tensor] = None
+        self.pending = 0
+
+
+class FlashAttentionSharedBias(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, bias, acc, causal, sm_scale):
+        assert q.shape[-1] == k.shape[-1] == v.shape[-1] and q.shape[-1] in {16, 32, 64, 128}
+        if sm_scale is None:
+            sm_scale = 1.0 / math.sqrt(q.shape[-1])
+        o, L = torch.ops.b200t5.attn_bias_fwd(q, k, v, bias, bool(causal), float(sm_scale))
+        ctx.save_for_backward(q, k, v, bias, o, L)
+        ctx.sm_scale, ctx.causal, ctx.acc = float(sm_scale), bool(causal), acc
+        acc.pending += 1
+        return o
+
+    @staticmethod
+    def backward(ctx, do, *ignored):
+        q, k, v, bias, o, L = ctx.saved_tensors
+        acc = ctx.acc
+        if acc.buf is None:
+            acc.buf = torch.zeros(bias.shape, dtype=torch.float32, device=bias.device)
+        if q.shape[-1] <= 64:
+            dq, dk, dv = torch.ops.b200t5.attn_bias_bwd_accum(o, do, q, k, v, bias, L, acc.buf, ctx.causal, ctx.sm_scale)
+        else:                                    # D = 128: the fp32 output is not implemented in that kernel; add in fp32 here
+            dq, dk, dv, ds = torch.ops.b200t5.attn_bias_bwd(o, do, q, k, v, bias, L, ctx.causal, ctx.sm_scale)
+            acc.buf += ds
+        acc.pending -= 1
+        g = None
+        if acc.pending == 0:                     # the last backward of the stack hands the one gradient to autograd
+            g, acc.buf = acc.buf.to(bias.dtype), None
+        return dq, dk, dv, g, None, None, None
+
+
+def flash_attention_v2_bias_shared(q, k, v, bias, acc: SharedBiasGrad, causal=False, sm_scale=None):
+    """`flash_attention_v2_bias` for a bias shared by several layers: same result, the bias gradient is accumulated in fp32
+    across the layers that were given the same `acc` and reaches autograd once (see SharedBiasGrad)."""
+    if bias is None or not bias.requires_grad:
+        return FlashAttentionAdditiveBias.apply(q, k, v, bias, causal, sm_scale)
+    return FlashAttentionSharedBias.apply(q, k, v, bias, acc, causal, sm_scale)
 
 
 def flash_attention_v2_bias(q, k, v, bias, causal=False, sm_scale=None):

@@ -65,6 +65,11 @@ enum { B200T5_F16 = 0, B200T5_BF16 = 1, B200T5_F32 = 2 };
  * elements); the sum over the broadcast dimensions is delivered unrounded, so that a data-parallel caller can all-reduce it
  * across ranks and round ONCE afterwards (flasht5_b200/data_parallel.py). */
 #define B200T5_ATTN_DBIAS_F32 2
+/* B200T5_ATTN_DBIAS_ACCUMULATE (with B200T5_ATTN_DBIAS_F32): dbias += the batch-summed dS instead of dbias = ...  The layers of a
+ * T5 stack share one position-bias tensor (reference modeling_flash_t5.py:452-455), so autograd adds L - 1 dense (H, M, N)
+ * gradients per stack; with this flag every layer's backward adds into ONE persistent fp32 buffer and the caller hands
+ * autograd a single gradient.  Causal-masked entries are left untouched. */
+#define B200T5_ATTN_DBIAS_ACCUMULATE 4
 
 typedef struct b200t5_attn_params {
     /* problem */

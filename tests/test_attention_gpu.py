@@ -543,3 +543,48 @@ def test_torch_compile_fullgraph_through_the_ops():
     for a, b_ in zip(outs[0][1:], outs[1][1:]):
         mx, rf = orc.error_metrics(b_, a.double())
         assert rf < 6e-3, (mx, rf)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(3, 4, 384, 384, 64, False), (2, 2, 300, 520, 32, True), (2, 2, 256, 256, 128, False)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_layer_shared_bias_gradient_accumulates_in_fp32(shape):
+    """L layers share one bias (reference modeling_flash_t5.py:452-455).  With one SharedBiasGrad the
+    layers' backward passes add their unrounded dBias into one fp32 buffer and autograd receives a single gradient: it must
+    equal the fp64 sum of the per-layer gradients at least as well as autograd's own sum of L rounded gradients does, and
+    dQ / dK / dV are untouched."""
+    from flasht5_b200 import SharedBiasGrad, flash_attention_v2_bias, flash_attention_v2_bias_shared
+    B, H, M, N, D, causal = shape
+    layers = 3
+    g = torch.Generator().manual_seed(21)
+    mk = lambda s: torch.randn(B, s, H, D, generator=g).to(torch.bfloat16).to(DEV).permute(0, 2, 1, 3)   # noqa: E731
+    qs, ks, vs, dos = [mk(M) for _ in range(layers)], [mk(N) for _ in range(layers)], [mk(N) for _ in range(layers)], [mk(M) for _ in range(layers)]
+    bias0 = torch.randn(1, H, M, N, generator=g).to(torch.bfloat16).to(DEV)
+
+    def run(shared):
+        bias = bias0.clone().requires_grad_(True)
+        acc = SharedBiasGrad()
+        leaves, loss = [], 0.0
+        for i in range(layers):
+            q, k, v = (t.detach().clone().requires_grad_(True) for t in (qs[i], ks[i], vs[i]))
+            o = flash_attention_v2_bias_shared(q, k, v, bias, acc, causal, 1.0) if shared else flash_attention_v2_bias(q, k, v, bias, causal, 1.0)
+            loss = loss + (o.float() * dos[i].float()).sum()
+            leaves += [q, k, v]
+        grads = torch.autograd.grad(loss, leaves + [bias])
+        assert acc.pending == 0 and acc.buf is None
+        return grads
+
+    plain, shared = run(False), run(True)
+    # dK, dV bitwise; dQ to its 16-bit partial sums
+    for i in range(layers):
+        assert torch.equal(plain[3 * i + 1], shared[3 * i + 1]) and torch.equal(plain[3 * i + 2], shared[3 * i + 2])
+        assert orc.error_metrics(shared[3 * i], plain[3 * i].double())[1] < 4e-3
+    # reference: fp64 sum of the per-layer gradients
+    ref = torch.zeros(1, H, M, N, dtype=torch.float64)
+    for i in range(layers):
+        ref += orc.attn_fwd_bwd(qs[i].cpu(), ks[i].cpu(), vs[i].cpu(), bias0.cpu(), dos[i].cpu(), causal, 1.0)[5].double()
+    e_plain = orc.error_metrics(plain[-1], ref)[1]
+    e_shared = orc.error_metrics(shared[-1], ref)[1]
+    assert shared[-1].dtype == torch.bfloat16
+    assert e_shared <= e_plain * 1.02 + 1e-6, (e_shared, e_plain)
+    assert e_shared < 6e-3
