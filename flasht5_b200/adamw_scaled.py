@@ -64,6 +64,7 @@ class AdamWScale(Optimizer):
                         correct_bias=correct_bias, use_state_dtype=use_state_dtype)
         super().__init__(params, defaults)
         self._chunk_cache = {}
+        self._table_cache = {}
 
     @staticmethod
     def _rms(tensor):
@@ -99,6 +100,7 @@ class AdamWScale(Optimizer):
         for group in self.param_groups:
             buckets = {}
             steps = []
+            active = []
             for p in group["params"]:
                 if p.grad is None:
                     continue
@@ -111,7 +113,14 @@ class AdamWScale(Optimizer):
                 if not (p.is_contiguous() and p.grad.is_contiguous() and state["exp_avg"].is_contiguous()
                         and state["exp_avg_sq"].is_contiguous()) or p.grad.dtype != p.dtype:
                     raise RuntimeError("AdamWScale needs contiguous parameters, gradients of the parameter dtype and contiguous states")
-                key = (p.device, p.dtype, state["exp_avg"].dtype, state["kahan_comp"] is not None)
+                active.append((p, state))
+            # The reference decides the Kahan path by the GROUP flag, read after every state of the group exists: one fp32
+            # parameter resets it for the whole group (:109-113), and then 16-bit parameters of that group -- which do own a
+            # compensation tensor if they were initialised first -- take the plain update too (:127-152 pass group["kahan_sum"]).
+            kahan_group = bool(group["kahan_sum"])
+            for p, state in active:
+                kahan = kahan_group and state["kahan_comp"] is not None
+                key = (p.device, p.dtype, state["exp_avg"].dtype, kahan)
                 buckets.setdefault(key, []).append((p, state))
             if steps:
                 torch._foreach_add_(steps, 1)              # the state tensors keep the reference's meaning (:120)
@@ -146,10 +155,22 @@ class AdamWScale(Optimizer):
             d.sqrt_numel = numels[i] ** 0.5
             d.ss_base, d.ss_floor = terms[t]
             d.neg_lr_wd = neg_lr_wd
-        # descriptor table -> device (pageable copy of a few KB; enqueued on the current stream, no synchronisation of the
-        # device: the bytes are staged by the driver before the call returns)
-        host = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8)
-        dev_table = host.to(device, non_blocking=False)
+        # descriptor table -> device through a cached PINNED staging buffer and a cached device buffer: a non-blocking copy
+        # enqueued on the current stream.  (A pageable source made every bucket of every step wait for all prior work of the
+        # stream -- ADVICE r1.)  The staging buffer is rewritten on the next step only after this copy has executed: an event
+        # wait that has long completed by then.
+        raw = bytes(table)
+        slot = self._table_cache.get((device, numels, kahan))
+        if slot is None or slot[0].numel() != len(raw):
+            slot = [torch.empty(len(raw), dtype=torch.uint8, pin_memory=True), torch.empty(len(raw), dtype=torch.uint8, device=device), None]
+            self._table_cache[(device, numels, kahan)] = slot
+        pinned, dev_table, copied = slot
+        if copied is not None:
+            copied.synchronize()
+        pinned.copy_(torch.frombuffer(bytearray(raw), dtype=torch.uint8))
+        dev_table.copy_(pinned, non_blocking=True)
+        slot[2] = torch.cuda.Event()
+        slot[2].record(torch.cuda.current_stream(device))
         nbytes = lib.b200t5_adamw_workspace_bytes(len(items), n_chunks)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
         round_step_to_p = (not correct_bias) and p_dtype in (torch.float16, torch.bfloat16)

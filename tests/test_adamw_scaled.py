@@ -281,3 +281,32 @@ def test_cuda_many_tensors_and_state_dict_round_trip():
         p1, m1, v1, _ = orc.step_like_reference(p0, gr, z, z, None, 1, 3e-3, 0.9, 0.999, 1e-6, wd)
         p2, m2, v2, _ = orc.step_like_reference(p1, gr, m1, v1, None, 2, 3e-3, 0.9, 0.999, 1e-6, wd)
         assert (params[j].detach().cpu() - p2).abs().max() <= 2e-6 * p2.abs().max() + 1e-9, j
+
+
+@pytest.mark.gpu
+def test_cuda_mixed_dtype_group_follows_the_group_kahan_flag():
+    """Reference :109-113, :127-152: one fp32 parameter resets the group's kahan_sum flag, and then the 16-bit parameters of
+    that group -- which own a compensation tensor when they were initialised first -- take the plain update as well
+    (ADVICE r1).  The bf16 parameter must end up bit-identical to the same parameter in a group with kahan_sum=False, and
+    several steps must not stall on the descriptor upload (pinned staging buffer reused across steps)."""
+    dev = "cuda:0"
+    g = torch.Generator().manual_seed(7)
+    w16 = torch.randn(5000, generator=g).to(torch.bfloat16)
+    w32 = torch.randn(3000, generator=g)
+    grads16 = [torch.randn(5000, generator=g).to(torch.bfloat16) for _ in range(3)]
+    grads32 = [torch.randn(3000, generator=g) for _ in range(3)]
+
+    def run(kahan):
+        a, b = torch.nn.Parameter(w16.clone().to(dev)), torch.nn.Parameter(w32.clone().to(dev))
+        opt = AdamWScale([a, b], lr=1e-2, kahan_sum=kahan)
+        for s in range(3):
+            a.grad, b.grad = grads16[s].to(dev), grads32[s].to(dev)
+            opt.step()
+        torch.cuda.synchronize()
+        return a.detach().cpu(), b.detach().cpu(), opt
+
+    a1, b1, opt1 = run(True)
+    a0, b0, _ = run(False)
+    assert opt1.param_groups[0]["kahan_sum"] is False                       # reset by the fp32 parameter
+    assert opt1.state[opt1.param_groups[0]["params"][0]]["kahan_comp"] is not None   # ... after the bf16 one got its tensor
+    assert torch.equal(a1, a0) and torch.equal(b1, b0)
