@@ -971,6 +971,8 @@ __device__ __forceinline__ void dbias_reduce_t_body(const uint16_t* __restrict__
                         const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
+                            // (unpack + FADD: the mixed-precision add.rn.f32.bf16 runs at a quarter of the FADD rate -- measured
+                            //  +13 us on the dQ conversion when it was tried here)
                             const float2 f = unpack2<kBf16>(w[e]);
                             acc[j][2 * e] += f.x;
                             acc[j][2 * e + 1] += f.y;
@@ -1034,7 +1036,7 @@ __global__ void __launch_bounds__(256) dbias_reduce_t_kernel(const uint16_t* __r
 
 // dQ conversion and the transposing dBias reduction in ONE launch (independent work; block-index split)
 template <int kD, bool kBf16, bool kOutF32>
-__global__ void __launch_bounds__(256) attn_bwd_post_fused_kernel(const uint4* __restrict__ dq_ws, int dq_groups, uint8_t* __restrict__ dq,
+__global__ void __launch_bounds__(256, 6) attn_bwd_post_fused_kernel(const uint4* __restrict__ dq_ws, int dq_groups, uint8_t* __restrict__ dq,
                                                                   int64_t sb, int64_t sh, int64_t sm, int B, int H, int M, float scale,
                                                                   int cvt_blocks, const uint16_t* __restrict__ ws, int m_pitch,
                                                                   void* __restrict__ dbias, int64_t o_sb, int64_t o_sh, int64_t o_sm,
