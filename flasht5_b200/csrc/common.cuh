@@ -77,36 +77,6 @@ __device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
 }
 
 // ------------------------------------------------------------------------------------------
-// 2^t on the FMA pipe for a pair of values (developer switch B200T5_EXP2_POLY, see attn_fwd.cu): the softmax loops issue
-// 16 384 ex2 per 128x128 tile against a MUFU rate of 16 / clk / SM -- 1 024 cycles, twice the tile's tensor-core time --
-// so moving a fraction of them to the FMA pipe (which has issue slots to spare during that phase) shortens the phase.
-//   t = j + f,  j = rint(t) (magic-number add),  f in [-0.5, 0.5];  2^f ~ cubic (max relative error 7.5e-5, well
-//   inside the 16-bit rounding of P);  2^j goes into the exponent field with an integer add.
-// Valid for t <= 127; t is clamped at -125 from below (result 2^-125 instead of a denormal / zero).
-// ------------------------------------------------------------------------------------------
-constexpr float kEx2PolyC0 = 0.9999280571937561f;
-constexpr float kEx2PolyC1 = 0.6932609677314758f;
-constexpr float kEx2PolyC2 = 0.2426111251115799f;
-constexpr float kEx2PolyC3 = 0.05517164245247841f;
-constexpr float kEx2Magic = 12582912.f;          // 1.5 * 2^23: (t + magic) holds rint(t) in its low mantissa bits
-constexpr float kEx2MinT = -125.f;
-
-__device__ __forceinline__ void ex2_poly_pair(float t0, float t1, float& e0, float& e1) {
-    t0 = fmaxf(t0, kEx2MinT);
-    t1 = fmaxf(t1, kEx2MinT);
-    const f32x2 t = f2_pack(t0, t1);
-    const f32x2 tj = f2_add(t, f2_pack(kEx2Magic, kEx2Magic));
-    const f32x2 fj = f2_add(tj, f2_pack(-kEx2Magic, -kEx2Magic));          // rint(t) as a float
-    const f32x2 f = f2_fma(fj, f2_pack(-1.f, -1.f), t);                     // t - rint(t)
-    f32x2 p = f2_fma(f2_pack(kEx2PolyC3, kEx2PolyC3), f, f2_pack(kEx2PolyC2, kEx2PolyC2));
-    p = f2_fma(p, f, f2_pack(kEx2PolyC1, kEx2PolyC1));
-    p = f2_fma(p, f, f2_pack(kEx2PolyC0, kEx2PolyC0));
-    float p0, p1, j0, j1;
-    f2_unpack(p, p0, p1);
-    f2_unpack(tj, j0, j1);
-    e0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(j0) << 23));
-    e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(j1) << 23));
-}
 
 template <int kRegs>
 __device__ __forceinline__ void setmaxnreg_inc() {
@@ -507,7 +477,7 @@ __device__ __forceinline__ float to_float16bit(uint16_t u) {
 
 // fp32 + one 16-bit half of a packed register in ONE instruction (sm_100 mixed-precision add, SASS FHADD.BF16 / .F16):
 // the dense-bias add without the separate unpack when sm_scale == 1 (x * 1 + b and x + b round identically).
-// Measured 109 / clk / SM (profiles/r1e_pipe_bench.txt).  Used by the B200T5_BIAS_FHADD developer builds.
+// Measured 109 / clk / SM (profiles/r1e_pipe_bench.txt).  Used by the forward (bias add when sm_scale == 1, sum of the rounded P); a quarter-rate instruction: not for streaming kernels.
 template <bool kBf16>
 __device__ __forceinline__ void add_f32_16x2(uint32_t packed, float c_lo, float c_hi, float& d_lo, float& d_hi) {
     if constexpr (kBf16) {

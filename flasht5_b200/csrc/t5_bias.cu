@@ -347,8 +347,8 @@ cudaError_t launch_rpe_band(const void* table, int64_t stride_b, int64_t stride_
 }
 
 // ------------------------------------------------------------------------------------------
-// Table gradient of the in-kernel relative-position bias straight from the 16-bit dS group surface (developer path,
-// B200T5_RPE_SKIP_CONST=2): only the tiles that are NOT entirely beyond a constant end of the bucket table carry
+// Table gradient of the in-kernel relative-position bias straight from the 16-bit dS group surface (the D <= 64 backward of
+// the in-kernel operator, B200T5_RPE_SKIP_LEVEL 2): only the tiles that are NOT entirely beyond a constant end of the bucket table carry
 // data (the attention backward keeps the others' dS in registers), so only those are read -- 3 of 8 tiles per query
 // block at S = 1024 -- and neither the dense (1,H,M,N) dBias scratch nor the producer's segmented sum is needed.
 // One CTA = one (key block, query block, head, group slice).  Thread t walks the wrapped diagonal w = t % 128 of its half of

@@ -3,7 +3,8 @@
 # GPU box pick a library with B200T5_LIB=... (tools/bwd_check.py, tools/gpu_perf.py).
 #   usage: tools/build_variant.sh [--headline] <name> "<extra nvcc flags>"
 # --headline: only the D = 64 / bf16 instantiations (-DB200T5_HEADLINE_ONLY): ~20 s to build and a small library.
-# Known switches: -DB200T5_EXP2_POLY=K  -DB200T5_FWD_TIMING  -DB200T5_BWD_TIMING  -DB200T5_RPE_SKIP_LEVEL=0|1|2
+# Known switches: -DB200T5_FWD_TIMING  -DB200T5_BWD_TIMING  -DB200T5_DEBUG_DEADLOCK  -DB200T5_RPE_SKIP_LEVEL=0|1|2
+#   backward ablations (wrong results by construction): -DB200T5_DBG_SKIP_EXP  _TRUNC_PACK  _SKIP_MATH  _SKIP_DS_TMA  _SKIP_DQ_TMA
 set -e
 HEADLINE=0
 if [ "$1" == "--headline" ]; then HEADLINE=1; shift; fi

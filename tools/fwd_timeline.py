@@ -1,8 +1,7 @@
 """Developer tool (GPU box): print the per-phase clock64 timeline of the forward kernel on one SM.
 Needs the timing build of the library (attn_fwd.cu compiled with -DB200T5_FWD_TIMING):
-    B200T5_LIB=$PWD/flasht5_b200/libb200t5_timing.so python tools/fwd_timeline.py [bias|nobias|rpe]
-B200T5_FWD_PERSIST=1 / B200T5_FWD_PINGPONG=1 in the environment select the persistent / two-query-tile kernels, which print
-their own timelines from the same build."""
+    tools/build_variant.sh --headline hl_fwdtiming "-DB200T5_FWD_TIMING"
+    B200T5_LIB=$PWD/flasht5_b200/libb200t5_hl_fwdtiming.so python tools/fwd_timeline.py [bias|nobias|rpe]"""
 import os
 import sys
 

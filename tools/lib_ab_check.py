@@ -1,7 +1,7 @@
 """Developer tool (GPU box): run a fixed set of seeded attention cases (forward + backward) through whichever library
 B200T5_LIB points at and either save the outputs (--save FILE) or compare them with a saved set (--compare FILE):
 O, LSE-dependent dK, dV must be bit-identical between two builds that only differ in scheduling; dQ and dBias are
-compared at 16-bit-rounding level.  With --tol (builds that change the arithmetic, e.g. -DB200T5_EXP2_POLY) every output
+compared at 16-bit-rounding level.  With --tol (builds that change the arithmetic) every output
 is compared at that level instead.  Also prints fwd / bwd times of the headline shape.
     python tools/lib_ab_check.py --save /tmp/base.pt ; B200T5_LIB=... python tools/lib_ab_check.py --compare /tmp/base.pt [--tol]"""
 import json
