@@ -258,9 +258,24 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
     uint64_t* box_free = all_done + 1;                  // [2] dS^T boxes of tile parity: dQ MMAs done + TMA reduce reads done (C -> compute)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::kTmemSlot);
 
+    if (warp == kWarpTma && lane == 0) {
+        // K and V are on the critical path of the prologue (TMA -> shared memory -> TMEM -> first S^T): their barrier is
+        // initialised by the producer lane itself and the loads leave before the CTA-wide setup barrier
+        // (V lands in the dQ staging tile, which is idle until the first dQ is drained: the drain warpgroup copies both
+        //  tiles into TMEM)
+        mbar_init(k_full, 1);
+        fence_mbar_init();
+        fence_proxy_async_smem();          // the barrier word was written through the generic proxy; TMA completes on it through the async one
+        tma_prefetch_desc(&p.map_k);
+        tma_prefetch_desc(&p.map_v);
+        if (n_iter > 0) {
+            mbar_arrive_expect_tx(k_full, 2 * C::kTileBytes);
+            tma_load_4d(smem + C::kK, &p.map_k, k_full, 0, col0, h, b);
+            tma_load_4d(smem + C::kDQ, &p.map_v, k_full, 0, col0, h, b);
+        }
+    }
     if (threadIdx.x == 0) {
         if ((smem_u32(smem) & 1023u) != 0) __trap();
-        mbar_init(k_full, 1);
         mbar_init(kt_ready, 4);
         for (int i = 0; i < C::kSlots; ++i) {
             mbar_init(qdo_full + i, 1);
@@ -286,7 +301,6 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
     if (warp == kWarpMmaA) tmem_alloc<512>(tmem_slot);
     if (warp == kWarpTma && lane == 0) {
         tma_prefetch_desc(&p.map_q);
-        tma_prefetch_desc(&p.map_k);
         tma_prefetch_desc(&p.map_do);
         tma_prefetch_desc(&p.map_dq);
         if (kBiasMode != 0) tma_prefetch_desc(&p.map_ds);
@@ -303,11 +317,7 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
         constexpr uint32_t hi_op = sdesc_hi(sbo, C::kSwizzle);       // Q, dO, K tiles (either major)
         if (warp == kWarpTma && lane == 0 && n_iter > 0) {
             // ---- K once; then the Q / dO ring (one slot = the 32 query rows of one sub-tile) ----
-            // (V lands in the dQ staging tile, which is idle until the first dQ is drained: the drain warpgroup copies both
-            //  tiles into TMEM)
-            mbar_arrive_expect_tx(k_full, 2 * C::kTileBytes);
-            tma_load_4d(smem + C::kK, &p.map_k, k_full, 0, col0, h, b);
-            tma_load_4d(smem + C::kDQ, &p.map_v, k_full, 0, col0, h, b);
+            // (K and V were requested before the setup barrier)
             const float* stat_bh = p.nl + ((int64_t)b * p.H + h) * (2 * (int64_t)p.m_pad);
             for (int u = 0; u < 2 * n_iter; ++u) {
                 const int s = u % C::kSlots;
@@ -695,15 +705,20 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
                 mbar_wait(all_done, 0);
                 tc_fence_after();
                 const uint32_t tm_acc = tmem_base + lane_off + (is_dv ? C::kColDV : C::kColDK) + c_first;
-#pragma unroll
-                for (int c0 = 0; c0 < kColsPer; c0 += 8) {
-                    uint32_t a[8];
+                // (all of the warpgroup's columns with one load + one wait, then the stores: kColsPer = 8, 16 or 32)
+                uint32_t acc[kColsPer];
+                if constexpr (kColsPer == 32) tmem_ld32(tm_acc, acc);
+                else if constexpr (kColsPer == 16) tmem_ld16(tm_acc, acc);
+                else
                     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                                 : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7])
-                                 : "r"(tm_acc + c0)
+                                 : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3]), "=r"(acc[4]), "=r"(acc[5]), "=r"(acc[6]), "=r"(acc[7])
+                                 : "r"(tm_acc)
                                  : "memory");
-                    tmem_ld_wait();
-                    if (key_ok) {
+                tmem_ld_wait();
+                if (key_ok) {
+#pragma unroll
+                    for (int c0 = 0; c0 < kColsPer; c0 += 8) {
+                        const uint32_t* a = acc + c0;
                         uint4 out;
                         out.x = pack2<kBf16>(__uint_as_float(a[0]) * sc, __uint_as_float(a[1]) * sc);
                         out.y = pack2<kBf16>(__uint_as_float(a[2]) * sc, __uint_as_float(a[3]) * sc);

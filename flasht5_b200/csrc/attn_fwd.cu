@@ -138,7 +138,7 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdKernelParams p) {
     }
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kTmemSlot);
 
-    if (threadIdx.x == 0) {
+    if (warp == 4 && lane == 0) {                 // the producer lane initialises the barriers: its first loads leave at once
         if ((smem_u32(smem) & 1023u) != 0) {
             printf("b200t5: dynamic smem base not 1024-byte aligned\n");
             __trap();
@@ -159,14 +159,25 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdKernelParams p) {
         mbar_init(bars.p_full, 4);
         mbar_init(bars.pv_done, 1);
         fence_mbar_init();
-    }
-    if (warp == 5) tmem_alloc<L::kTmemCols>(tmem_slot);
-    if (warp == 4 && lane == 0) {
+        fence_proxy_async_smem();                 // barrier words: written through the generic proxy, completed through the async one
         tma_prefetch_desc(&p.map_q);
         tma_prefetch_desc(&p.map_k);
         tma_prefetch_desc(&p.map_v);
         if (kBiasMode == 1) tma_prefetch_desc(&p.map_bias);
+        if (num_tiles > 0) {
+            // Q and the first K tile are on the critical path of the prologue (first S ready ~2 900 cycles after launch): they
+            // leave before the CTA-wide setup barrier, while warp 5 allocates TMEM
+            mbar_arrive_expect_tx(bars.q_full, L::kTileBytes);
+#pragma unroll
+            for (int bx = 0; bx < L::kBoxes; ++bx)
+                tma_load_4d(smem + L::kQ + bx * L::kBoxBytes, &p.map_q, bars.q_full, bx * 64, row0, h, b);
+            mbar_arrive_expect_tx(bars.k_full + 0, L::kTileBytes);
+#pragma unroll
+            for (int bx = 0; bx < L::kBoxes; ++bx)
+                tma_load_4d(smem + L::kK + bx * L::kBoxBytes, &p.map_k, bars.k_full + 0, bx * 64, 0, h, b);
+        }
     }
+    if (warp == 5) tmem_alloc<L::kTmemCols>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -198,20 +209,18 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdKernelParams p) {
         // =============================== control warps ===============================
         setmaxnreg_dec<48>();
         if (warp == 4 && lane == 0 && num_tiles > 0) {
-            // ---- Q / K / V producer ----
-            mbar_arrive_expect_tx(bars.q_full, L::kTileBytes);
-#pragma unroll
-            for (int bx = 0; bx < L::kBoxes; ++bx)
-                tma_load_4d(smem + L::kQ + bx * L::kBoxBytes, &p.map_q, bars.q_full, bx * 64, row0, h, b);
+            // ---- Q / K / V producer (Q and K tile 0 were requested before the setup barrier) ----
             for (int j = 0; j < num_tiles; ++j) {
                 const int s = j % kKVStages;
                 const uint32_t par = ((j / kKVStages) & 1) ^ 1;
-                mbar_wait_producer(bars.k_empty + s, par);
-                mbar_arrive_expect_tx(bars.k_full + s, L::kTileBytes);
+                if (j > 0) {
+                    mbar_wait_producer(bars.k_empty + s, par);
+                    mbar_arrive_expect_tx(bars.k_full + s, L::kTileBytes);
 #pragma unroll
-                for (int bx = 0; bx < L::kBoxes; ++bx)
-                    tma_load_4d(smem + L::kK + s * L::kTileBytes + bx * L::kBoxBytes, &p.map_k, bars.k_full + s,
-                                bx * 64, j * kBN, h, b);
+                    for (int bx = 0; bx < L::kBoxes; ++bx)
+                        tma_load_4d(smem + L::kK + s * L::kTileBytes + bx * L::kBoxBytes, &p.map_k, bars.k_full + s,
+                                    bx * 64, j * kBN, h, b);
+                }
                 mbar_wait_producer(bars.v_empty + s, par);
                 mbar_arrive_expect_tx(bars.v_full + s, L::kTileBytes);
 #pragma unroll
