@@ -7,49 +7,51 @@
 // through shared memory) moved ~430 KB per 128x128 tile through the 128 B/clk shared-memory port (3 400 of its 3 900
 // cycles per tile), and its stages ran back to back.  Here the CTA computes the TRANSPOSED score tile,
 //     S^T = K Q^T   and   dP^T = V dO^T          (TMEM lanes = keys, columns = queries),
-// with K and V held in TMEM for the whole CTA as the A operands (written once with tcgen05.st), so that
+// with K and V held in TMEM for the whole CTA as the A operands (TMA -> shared memory -> tcgen05.st, once), so that
 //     dV += P^T dO   and   dK += dS^T Q
-// take P^T / dS^T straight FROM TMEM (the compute warps write them back over S^T / dP^T as packed 16-bit pairs), and
+// take P^T / dS^T straight FROM TMEM (the compute warps write them as packed 16-bit pairs into columns of their own), and
 // only dS goes to shared memory -- once, in the layout the dQ MMA reads as an MN-major A operand and the TMA unit
-// reduces into the (transposed) dBias surface.  Shared-memory traffic per tile drops from ~430 KB to ~210 KB (+96 KB
+// reduces into the (transposed) dBias surface.  Shared-memory traffic per tile drops from ~430 KB to ~210 KB (+64 KB
 // with a dense bias).
 //
 // One CTA = one (batch, head, 128-key block); it walks the query sequence in 128-row tiles, each processed as four
-// 32-query sub-tiles t = 4k + j over FOUR S^T / dP^T buffers in TMEM.  Compute warpgroup j owns buffer j (one sub-tile per
-// tile), and the MMAs are issued by two warps so that neither waits on the other's barriers:
+// 32-query sub-tiles t = 4k + j.  Compute warpgroup j owns sub-tile j of every tile; S^T / dP^T of sub-tile t land in TMEM
+// buffer t & 1 and are released as soon as the warpgroup has them in registers:
 //
-//   MMA warps A0-A3 one per sub-tile j: wait Q / dO slot, S^T / dP^T buffer t & 1 free -> S^T(t), dP^T(t)
+//   TMA producer    K, V once (requested before the setup barrier); ring of 64-query slots = Q rows + dO rows + one record of
+//                   row statistics [-L log2e | -delta] written by the pre-kernel: three operations per slot
+//   MMA warps A0-A3 one per sub-tile j: wait slot, wait buffer t & 1 free -> S^T(t), dP^T(t)   (8 MMAs, N = 32, TS)
 //                   (four warps: a blocking barrier probe costs ~100 cycles even when the phase has long completed, and one
 //                    warp doing two or three of them per sub-tile set the pace of the whole CTA at ~550 cycles per sub-tile)
-//   compute WG j    wait S,dP(t) -> P, dS in registers -> P^T, dS^T -> TMEM, dS -> smem -> signal
-//   MMA warp B      for t: wait P,dS(t) -> dV,dK(t) -> free buffer j and the Q / dO slot
-//   warp C          for t: wait P,dS(t) -> TMA reduce-add of the dS^T box into the dBias surface;  after j = 3: dQ(k)
-//   drain WG        dQ(k): TMEM -> 16-bit staging tile -> TMA reduce-add into the dQ group surface
-// The compute warps never synchronise with each other: every thread arrives on the P,dS barrier of its buffer by itself, and
-// the row statistics come from global memory in the form the kernel consumes (written by the pre-kernel).
+//   compute WG j    wait S,dP(t) -> registers, release the buffer -> P, dS (packed f32x2 math) -> P^T, dS^T -> its own TMEM
+//                   columns, dS^T -> its shared-memory box -> per-thread arrive (no barrier inside the warpgroup)
+//   MMA warps B0/B1 even / odd t: wait P,dS(t), wait the other warp's token (dV / dK accumulate in sub-tile order: bitwise
+//                   reproducible) -> dV,dK(t) (4 MMAs, N = D, TS) -> free the warpgroup's columns and the Q / dO slot
+//   warp C          per tile: dS^T boxes -> dBias surface (TMA reduce-add / store; skipped for constant relative-position
+//                   sub-tiles), then dQ(k) = dS K (8 MMAs, SS)
+//   drain WG        prologue: K, V shared memory -> TMEM; per tile dQ(k): TMEM -> 16-bit staging tile -> TMA reduce-add into the
+//                   dQ group surface
 //
-// (Measured on the way here -- profiles/r2b_*: (1) two 64-query half tiles over two buffers left every warpgroup idle ~900
-//  cycles per tile, because S^T(t+2) lands in the buffer of S^T(t) and cannot be issued before dV,dK(t) consumed P^T(t);
-//  (2) four buffers with two warpgroups and one MMA warp: the warpgroup's own chain wait -> math -> tcgen05.st -> fences ->
-//  barrier (~1 100 cycles per sub-tile, of which ~500 are math) and the single MMA thread's blocking waits (~90 cycles per
-//  completed mbarrier probe) set the pace at 3 300 cycles per tile against 1 424 cycles of tensor work; tools/micro/mma_rate.cu
-//  shows TS-mode MMAs run at the ideal rate down to N = 16 while SS-mode ones are bound by the 128 B/clk shared-memory port.)
+// (Measured on the way here -- profiles/r2b_*, r2c_bwd_v3_ablations.txt: (1) two 64-query half tiles over two buffers with P^T
+//  aliased over S^T left every warpgroup idle ~900 cycles per tile: S^T(t+2) could not be issued before dV,dK(t) had consumed
+//  P^T(t); (2) two warpgroups and one MMA warp: the single MMA thread's blocking waits set the pace at 3 300 cycles per tile
+//  against 1 424 cycles of tensor work; (3) a ring of eleven 32-query slots: the producer lane's four TMA operations per
+//  sub-tile (~650 cycles) set the pace; (4) K, V from global memory straight to TMEM: 4 000 cycles of prologue per CTA.
+//  tools/micro/mma_rate.cu shows TS-mode MMAs run at the ideal rate down to N = 16 while SS-mode ones are bound by the
+//  128 B/clk shared-memory port.)
 //
 //   warps 0-15  : compute warpgroups 0-3 (thread = key row)     warps 16-19 : K, V -> TMEM (prologue), dQ drain
-//   warp 20 : TMA producer K, Q / dO ring   warps 21, 24, 26, 27 : MMA warps A (S^T, dP^T of sub-tile j = 0..3 of every tile)
-//   warps 22, 25 : MMA warps B (dV, dK of even / odd sub-tiles)   warp 23 : warp C (dQ, dS out)
+//   warp 20 : TMA producer                  warps 21, 24, 26, 27 : MMA warps A (S^T, dP^T of sub-tile j = 0..3 of every tile)
+//   warps 22, 25 : MMA warps B (dV, dK of even / odd sub-tiles)   warp 23 : warp C (dS out, dQ)
 //
 // TMEM columns: S^T 2 x [32] in [0,64) | dP^T 2 x [32] in [64,128) | P^T 4 x [16] in [128,192) | dS^T 4 x [16] in [192,256) |
 //               dV [256,256+D) | dK [256+D,256+2D) | dQ [256+2D,256+3D) | K [448,448+D/2) | V [480,480+D/2).
-// S^T / dP^T buffers are free again as soon as the compute warps have them in registers, so warp A refills them at once and a
-// warpgroup's next S^T never waits for the dV / dK MMAs of its previous sub-tile (with P^T aliased over S^T it did: ~1 800
-// cycles per tile, profiles/r2b_*); P^T / dS^T have their own columns, one set per warpgroup.
 //
-// Bias modes: 0 none | 1 dense bias, read from a REPACKED copy that api.cu makes in the workspace: for every (key block,
-// 32-query sub-tile) the 128 x 32 values are stored as 4 x [128 keys][8 queries], so that thread = key row fetches its 32
-// bias values with four fully coalesced 16-byte global loads, one sub-tile ahead, with no shared-memory staging at all |
-// 3 T5 relative-position bias from the band.
-// dS leaves the CTA transposed: the surface is (G, H, N, M) and the finalize kernel transposes while it reduces.
+// Bias modes: 0 none | 1 dense bias, read from a REPACKED copy that the pre-kernel makes in the workspace: for every (key
+// block, 32-query sub-tile) the 128 x 32 values are stored as 4 x [128 keys][8 queries], so that thread = key row fetches
+// its 32 bias values with four fully coalesced 16-byte cp.async copies one tile ahead (into shared memory: in registers
+// they would be live across a whole sub-tile) | 3 T5 relative-position bias from the band in shared memory.
+// dS leaves the CTA transposed: the surface is (G, H, N, M) and the post-kernel transposes while it reduces.
 #include "common.cuh"
 #include "kernels.h"
 
