@@ -93,7 +93,7 @@ struct Bwd3Cfg {
     static constexpr int kBand = kDQ + kTileBytes;                     // relative-position band (mode 3) / bias staging (mode 1), 32 KB
     static constexpr int kStats = kBand + (kBiasMode == 0 ? 0 : 32768);                     // [kSlots][2][64] fp32: -L*log2e, -delta of the slot's queries
     static constexpr int kBars = kStats + kSlots * 2 * kSlotRows * 4;
-    static constexpr int kNumBars = 2 + 2 * kSlots + 6 * kNSub + 3 + 2 + 2;
+    static constexpr int kNumBars = 2 + 2 * kSlots + 5 * kNSub + 3 + 2 + 2;
     static constexpr int kTmemSlot = kBars + kNumBars * 8;
     static constexpr int kTotal = kTmemSlot + 16;
     static_assert(kTotal <= 232448, "shared memory budget");
@@ -251,9 +251,8 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
     // uneven).  With one barrier set per tile parity a warpgroup would have to be two tiles ahead of C, which box_free forbids.
     uint64_t* pds_full = sdp_full + kNSub;
     uint64_t* pds_free = pds_full + 2 * kNSub;              // [4] dV, dK MMAs reading P^T / dS^T of j completed (MMA B -> compute j)
-    uint64_t* s_empty = pds_free + kNSub;               // [4] compute j has S^T of its sub-tile in registers  (compute j -> MMA A)
-    uint64_t* dp_empty = s_empty + kNSub;               // [4] ... and dP^T
-    uint64_t* dq_full = dp_empty + kNSub;
+    uint64_t* s_empty = pds_free + kNSub;               // [4] compute j has S^T and dP^T of its sub-tile in registers  (compute j -> MMA A)
+    uint64_t* dq_full = s_empty + kNSub;
     uint64_t* dq_empty = dq_full + 1;
     uint64_t* all_done = dq_empty + 1;                  // every MMA of the CTA completed (single phase: the epilogue's gate; B and C commit)
     uint64_t* b_turn = all_done + 3;                    // [2] B0 <-> B1 token: the dV / dK MMAs are issued in sub-tile order (bitwise reproducible sums)
@@ -294,7 +293,6 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
             mbar_init(pds_full + kNSub + i, 128);
             mbar_init(pds_free + i, 1);
             mbar_init(s_empty + i, 4);
-            mbar_init(dp_empty + i, 4);
         }
         mbar_init(dq_full, 1);
         mbar_init(dq_empty, 4);
