@@ -454,7 +454,8 @@ static int attn_bwd_impl(const b200t5_attn_params* p, const b200t5_rpe_params* r
     const uint32_t qrows = w.transposed ? 64 : 128;         // the v3 kernel loads Q / dO per 64-query half tile
     if ((rc = make_map_4d(&kp.map_q, p->q, 2, dt, p->D, p->M, p->H, p->B, p->q_strides[2], p->q_strides[1], p->q_strides[0], boxd, qrows, "q"))) return rc;
     if ((rc = make_map_4d(&kp.map_k, p->k, 2, dt, p->D, p->N, p->H, p->B, p->k_strides[2], p->k_strides[1], p->k_strides[0], boxd, 128, "k"))) return rc;
-    if ((rc = make_map_4d(&kp.map_v, p->v, 2, dt, p->D, p->N, p->H, p->B, p->v_strides[2], p->v_strides[1], p->v_strides[0], boxd, 128, "v"))) return rc;
+    // (v3: V travels through the Q / dO ring as two 64-key halves)
+    if ((rc = make_map_4d(&kp.map_v, p->v, 2, dt, p->D, p->N, p->H, p->B, p->v_strides[2], p->v_strides[1], p->v_strides[0], boxd, w.transposed ? 64 : 128, "v"))) return rc;
     if ((rc = make_map_4d(&kp.map_do, p->dout, 2, dt, p->D, p->M, p->H, p->B, p->do_strides[2], p->do_strides[1], p->do_strides[0], boxd, qrows, "dout"))) return rc;
     if ((rc = make_map_4d(&kp.map_dq, dq_ws, 2, dt, p->D, p->M, p->H, (uint64_t)w.dq_groups * p->B, p->D, (int64_t)p->M * p->D, (int64_t)p->H * p->M * p->D, boxd, 128, "dq group surface", true))) return rc;
     kp.dq_groups = w.dq_groups;

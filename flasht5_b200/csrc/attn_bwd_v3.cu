@@ -198,10 +198,11 @@ __device__ __forceinline__ void v3_chunk(const uint32_t (&sr)[16], const uint32_
 }  // namespace
 
 #ifdef B200T5_BWD_TIMING
+__device__ long long g_bwd3_item_ts[8][20];    // [CTA 0..7][item boundary]: clock64 of compute thread 0 at the start of every item (+ the end)
 __device__ long long g_bwd3_ts[8][32][8];      // [role: wg0..wg3, mma B, drain, mma A, producer][iteration][slot]
 #define BWD3_TS(role, k, slot)                                                          \
     do {                                                                                \
-        if (blockIdx.x == 777 && (k) < 32) g_bwd3_ts[role][k][slot] = clock64();        \
+        if (blockIdx.x == 7 && it == 1 && (k) < 32) g_bwd3_ts[role][k][slot] = clock64();   \
     } while (0)
 #else
 #define BWD3_TS(role, k, slot) do { } while (0)
@@ -220,23 +221,42 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    // ---- work decode: batch fastest (bias tiles shared in L2), long key blocks first when causal ----
+    // ---- PERSISTENT: the CTA walks work items (batch, head, key block) item = blockIdx.x, + gridDim.x, ...; barriers, TMEM and
+    //      the ring live across items, every role keeps two running counters (it: non-empty items done, kb: tiles done) from
+    //      which all barrier parities follow.  What this buys over one CTA per item: no per-item launch / setup / teardown, and
+    //      the tail of item i (last dQ drain, dK / dV write-out) overlaps the prologue of item i + 1 (K, V -> TMEM, first S^T).
+    //      Work decode: batch fastest (bias tiles shared in L2), long key blocks first when causal ----
     const int nnb = p.num_n_blocks;
-    int bid = blockIdx.x;
-    const int b = bid % p.B;
-    bid /= p.B;
-    const int nb = kCausal ? (bid % nnb) : (nnb - 1 - bid % nnb);
-    const int h = bid / nnb;
-    const int col0 = nb * kBN;
     const int pseq = p.N - p.M;
-
-    int i_start = 0;
-    if (kCausal) {
-        const int first_row = col0 - pseq;                      // first query row that sees key col0
-        i_start = first_row <= 0 ? 0 : first_row / kBM;
+    const int n_items = p.B * p.H * nnb;
+    struct Item { int b, nb, h, col0, i_start, n_iter; };
+    auto decode = [&](int item) {
+        Item w;
+        int bid = item;
+        w.b = bid % p.B;
+        bid /= p.B;
+        w.nb = kCausal ? (bid % nnb) : (nnb - 1 - bid % nnb);
+        w.h = bid / nnb;
+        w.col0 = w.nb * kBN;
+        w.i_start = 0;
+        if (kCausal) {
+            const int first_row = w.col0 - pseq;                // first query row that sees key col0
+            w.i_start = first_row <= 0 ? 0 : first_row / kBM;
+        }
+        w.n_iter = p.num_m_blocks > w.i_start ? p.num_m_blocks - w.i_start : 0;
+        return w;
+    };
+    int it = 0, kb = 0;                                         // non-empty items / tiles this CTA has been through
+#define B200T5_ITEM_BEGIN                                                                                                   \
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {                                                        \
+        const Item w_ = decode(item);                                                                                       \
+        const int b = w_.b, nb = w_.nb, h = w_.h, col0 = w_.col0, i_start = w_.i_start, n_iter = w_.n_iter, T = kNSub * n_iter; \
+        (void)b; (void)nb; (void)h; (void)col0; (void)i_start; (void)T;
+#define B200T5_ITEM_END                                                                                                     \
+        kb += n_iter;                                                                                                       \
+        ++it;                                                                                                               \
     }
-    const int n_iter = p.num_m_blocks > i_start ? p.num_m_blocks - i_start : 0;
-    const int T = kNSub * n_iter;
+    const Item first_item = decode(blockIdx.x);
 
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kBars);
     uint64_t* k_full = bars;
@@ -265,22 +285,27 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
         // (V lands in the dQ staging tile, which is idle until the first dQ is drained: the drain warpgroup copies both
         //  tiles into TMEM)
         mbar_init(k_full, 1);
+        mbar_init(qdo_full + 0, 1);
         fence_mbar_init();
-        fence_proxy_async_smem();          // the barrier word was written through the generic proxy; TMA completes on it through the async one
+        fence_proxy_async_smem();          // the barrier words were written through the generic proxy; TMA completes on them through the async one
         tma_prefetch_desc(&p.map_k);
         tma_prefetch_desc(&p.map_v);
-        if (n_iter > 0) {
-            mbar_arrive_expect_tx(k_full, 2 * C::kTileBytes);
-            tma_load_4d(smem + C::kK, &p.map_k, k_full, 0, col0, h, b);
-            tma_load_4d(smem + C::kDQ, &p.map_v, k_full, 0, col0, h, b);
+        if (first_item.n_iter > 0) {
+            mbar_arrive_expect_tx(k_full, C::kTileBytes);
+            tma_load_4d(smem + C::kK, &p.map_k, k_full, 0, first_item.col0, first_item.h, first_item.b);
+            // V travels through the Q / dO ring like a half tile (ring position 0 = slot 0): keys 0-63 in the slot's Q rows, keys
+            // 64-127 in its dO rows
+            mbar_arrive_expect_tx(qdo_full + 0, 2 * C::kSlotBytes);
+            tma_load_4d(smem + C::kQ, &p.map_v, qdo_full + 0, 0, first_item.col0, first_item.h, first_item.b);
+            tma_load_4d(smem + C::kDO, &p.map_v, qdo_full + 0, 0, first_item.col0 + C::kSlotRows, first_item.h, first_item.b);
         }
     }
     if (threadIdx.x == 0) {
         if ((smem_u32(smem) & 1023u) != 0) __trap();
         mbar_init(kt_ready, 4);
         for (int i = 0; i < C::kSlots; ++i) {
-            mbar_init(qdo_full + i, 1);
-            mbar_init(qdo_empty + i, 2);                  // one commit from each B warp (the slot's even and odd sub-tile)
+            if (i > 0) mbar_init(qdo_full + i, 1);        // (slot 0: initialised by the producer lane above)
+            mbar_init(qdo_empty + i, 2);                  // one commit from each B warp (the slot's even and odd sub-tile); V: two arrivals of warpgroup 0
         }
         mbar_init(all_done, 3);                           // the two B warps and warp C
         mbar_init(box_free + 0, 2);
@@ -315,15 +340,38 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
         setmaxnreg_dec<32>();
         constexpr uint32_t sbo = 8 * C::kRowBytes;
         constexpr uint32_t hi_op = sdesc_hi(sbo, C::kSwizzle);       // Q, dO, K tiles (either major)
-        if (warp == kWarpTma && lane == 0 && n_iter > 0) {
-            // ---- K once; then the Q / dO ring (one slot = the 32 query rows of one sub-tile) ----
-            // (K and V were requested before the setup barrier)
+        if (warp == kWarpTma && lane == 0) {
+            // ---- per item: K, V (the first item's were requested before the setup barrier); then the Q / dO ring ----
+            B200T5_ITEM_BEGIN
+            if (n_iter == 0) continue;
+            // Ring positions: item `it` takes position 2 kb + it for its V tile and 2 kb + it + 1 + u for its half tile u.
+            if (!(it == 0 && item == static_cast<int>(blockIdx.x))) {
+                // V: as soon as a ring slot is free (well before the item boundary); it waits there until warpgroup 0 copies it
+                // into TMEM.  K: its shared-memory tile is free once every dQ MMA of the previous item completed.
+                const int pv = 2 * kb + it, sv = pv % C::kSlots;
+                mbar_wait_producer(qdo_empty + sv, ((pv / C::kSlots) & 1) ^ 1);
+                mbar_arrive_expect_tx(qdo_full + sv, 2 * C::kSlotBytes);
+                tma_load_4d(smem + C::kQ + sv * C::kSlotBytes, &p.map_v, qdo_full + sv, 0, col0, h, b);
+                tma_load_4d(smem + C::kDO + sv * C::kSlotBytes, &p.map_v, qdo_full + sv, 0, col0 + C::kSlotRows, h, b);
+                mbar_arrive_expect_tx(k_full, C::kTileBytes);
+                if (it > 0) mbar_wait(all_done, (it - 1) & 1);
+                tma_load_4d(smem + C::kK, &p.map_k, k_full, 0, col0, h, b);
+            }
+            // K of the next item: into L2 now, so that its TMA load at the item boundary (which is on the critical path: the tile
+            // can only land once this item's dQ MMAs are done with K) starts from L2 instead of HBM.  (V is loaded early.)
+            for (int nxt = item + static_cast<int>(gridDim.x); nxt < n_items; nxt += gridDim.x) {
+                const Item wn = decode(nxt);
+                if (wn.n_iter == 0) continue;
+                tma_prefetch_l2_4d(&p.map_k, 0, wn.col0, wn.h, wn.b);
+                break;
+            }
             const float* stat_bh = p.nl + ((int64_t)b * p.H + h) * (2 * (int64_t)p.m_pad);
             for (int u = 0; u < 2 * n_iter; ++u) {
-                const int s = u % C::kSlots;
+                const int ug = 2 * kb + it + 1 + u;                     // ring position over the whole CTA
+                const int s = ug % C::kSlots;
                 const int m0 = (i_start + (u >> 1)) * kBM + (u & 1) * C::kSlotRows;
                 BWD3_TS(7, u, 0);
-                mbar_wait_producer(qdo_empty + s, ((u / C::kSlots) & 1) ^ 1);
+                mbar_wait_producer(qdo_empty + s, ((ug / C::kSlots) & 1) ^ 1);
                 BWD3_TS(7, u, 1);
                 mbar_arrive_expect_tx(qdo_full + s, 2 * C::kSlotBytes + 2 * C::kSlotRows * 4);
                 tma_load_4d(smem + C::kQ + s * C::kSlotBytes, &p.map_q, qdo_full + s, 0, m0, h, b);
@@ -332,7 +380,8 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
                 bulk_load_1d(reinterpret_cast<float*>(smem + C::kStats) + s * (2 * C::kSlotRows), stat_bh + (m0 / C::kSlotRows) * (2 * C::kSlotRows),
                              2 * C::kSlotRows * 4, qdo_full + s);
             }
-        } else if ((warp == kWarpMmaA || warp == kWarpMmaA1 || warp == kWarpMmaA2 || warp == kWarpMmaA3) && n_iter > 0) {
+            B200T5_ITEM_END
+        } else if (warp == kWarpMmaA || warp == kWarpMmaA1 || warp == kWarpMmaA2 || warp == kWarpMmaA3) {
             // ---- MMA warp A: S^T = K Q^T and dP^T = V dO^T of every sub-tile (A operands K, V in TMEM) ----
             // (the whole warp runs the loop so that descriptor arithmetic stays warp-uniform; one elected lane issues)
             const bool leader = elect_one();
@@ -341,18 +390,21 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
             const uint32_t do_lo0 = sdesc_lo(smem_u32(smem + C::kDO), 16);
             const uint32_t tm_kt = tmem_base + C::kColKt;
             const uint32_t tm_vt = tmem_base + C::kColVt;
-            mbar_wait(kt_ready, 0);
             const int j_mine = warp == kWarpMmaA ? 0 : (warp == kWarpMmaA1 ? 1 : (warp == kWarpMmaA2 ? 2 : 3));
+            B200T5_ITEM_BEGIN
+            if (n_iter == 0) continue;
+            mbar_wait(kt_ready, it & 1);
             for (int t = j_mine; t < T; t += kNSub) {
-                const int k = t >> 2, j = t & 3;
+                const int j = t & 3;
+                const int tg = 4 * kb + t;                              // sub-tile count over the whole CTA
                 if (lane == 0) BWD3_TS(6, t, 0);
-                const int u = t >> 1;                                   // half-tile = ring slot use
+                const int u = (tg >> 1) + it + 1;                       // ring position of the half tile
                 mbar_wait(qdo_full + (u % C::kSlots), (u / C::kSlots) & 1);
                 if (lane == 0) BWD3_TS(6, t, 1);
-                if (t >= 2) {
-                    // buffer t & 1 held sub-tile t - 2 (warpgroup (j + 2) & 3, tile (t - 2) >> 2): in registers by now?
+                if (tg >= 2) {
+                    // buffer t & 1 held sub-tile tg - 2 (warpgroup (j + 2) & 3): in registers by now?
                     const int jp = (j + 2) & 3;
-                    const uint32_t par = ((t - 2) >> 2) & 1;
+                    const uint32_t par = ((tg - 2) >> 2) & 1;
                     mbar_wait(s_empty + jp, par);           // (S^T and dP^T are loaded together: one barrier)
                 }
                 tc_fence_after();
@@ -372,29 +424,32 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
                 __syncwarp();
                 if (lane == 0) BWD3_TS(6, t, 3);
             }
-        } else if ((warp == kWarpMmaB || warp == kWarpMmaB1) && n_iter > 0) {
+            B200T5_ITEM_END
+        } else if (warp == kWarpMmaB || warp == kWarpMmaB1) {
             // ---- MMA warps B0 / B1: dV += P^T dO, dK += dS^T Q of the even / odd sub-tiles (A operands from TMEM).  The
             //      accumulators were zero-filled by the drain warpgroup (kt_ready): the two warps' first MMAs come in any order ----
-            mbar_wait(kt_ready, 0);
             const bool leader = elect_one();
             constexpr uint32_t idesc_dkv = make_idesc(kBf16, 128, kD, false, true);    // A tmem, B MN-major
             const uint32_t q_mn_lo0 = sdesc_lo(smem_u32(smem + C::kQ), C::kSubTileBytes);
             const uint32_t do_mn_lo0 = sdesc_lo(smem_u32(smem + C::kDO), C::kSubTileBytes);
             const uint32_t tm_dv = tmem_base + C::kColDV;
             const uint32_t tm_dk = tmem_base + C::kColDK;
+            B200T5_ITEM_BEGIN
+            if (n_iter == 0) continue;
             for (int t = (warp == kWarpMmaB ? 0 : 1); t < T; t += 2) {
-                const int k = t >> 2, j = t & 3;
+                const int j = t & 3;
+                const int tg = 4 * kb + t, kg = kb + (t >> 2);          // counts over the whole CTA
                 if (lane == 0) BWD3_TS(4, t, 0);
-                mbar_wait(pds_full + (k & 1) * kNSub + j, (k >> 1) & 1);
+                mbar_wait(pds_full + (kg & 1) * kNSub + j, (kg >> 1) & 1);
                 tc_fence_after();
                 if (lane == 0) BWD3_TS(4, t, 1);
-                const int slot = (t >> 1) % C::kSlots;
+                const int slot = ((tg >> 1) + it + 1) % C::kSlots;      // ring position of the half tile
                 const uint32_t so = (slot * 2 + (t & 1)) * (C::kSubTileBytes >> 4);
                 const uint32_t tm_p = tmem_base + C::kColP + j * 16;         // P^T  (packed 16-bit pairs)
                 const uint32_t tm_ds = tmem_base + C::kColDS + j * 16;       // dS^T (packed 16-bit pairs)
                 // the other B warp has issued sub-tile t - 1: both accumulate into the same dV / dK columns, and a fixed order
                 // of the fp32 additions makes dK, dV bitwise reproducible (strict alternation: nobody lags a phase)
-                if (t > 0) mbar_wait(b_turn + (t & 1), ((t - 1) >> 1) & 1);
+                if (tg > 0) mbar_wait(b_turn + (tg & 1), ((tg - 1) >> 1) & 1);
                 if (leader) {
                     // (K dimension = the 32 queries of this sub-tile)
 #pragma unroll
@@ -407,13 +462,14 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
                     // Q / dO slot: the S^T / dP^T MMAs of warp A that read it completed before the compute warps could produce
                     // the P^T this warp just consumed, so this commit covers every reader of the slot
                     umma_commit(qdo_empty + slot);
-                    if (t >= T - 2) umma_commit(all_done);          // the last sub-tile of this warp (T is a multiple of 4)
-                    mbar_arrive(b_turn + ((t + 1) & 1));
+                    if (t >= T - 2) umma_commit(all_done);          // the last sub-tile of this warp in this item (T is a multiple of 4)
+                    mbar_arrive(b_turn + ((tg + 1) & 1));
                 }
                 __syncwarp();
                 if (lane == 0) BWD3_TS(4, t, 3);
             }
-        } else if (warp == kWarpC && n_iter > 0) {
+            B200T5_ITEM_END
+        } else if (warp == kWarpC) {
             // ---- warp C: dS^T boxes -> dBias surface (TMA reduce-add / store), and dQ = dS K once per tile ----
             const bool leader = elect_one();
             constexpr uint32_t idesc_dq = make_idesc(kBf16, 128, kD, true, true);      // A, B MN-major
@@ -421,18 +477,21 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
             const uint32_t k_mn_lo = sdesc_lo(smem_u32(smem + C::kK), C::kTileBytes);
             const uint32_t ds_mn_lo0 = sdesc_lo(smem_u32(smem + C::kDS), kBoxBytes);   // A = dS (M = queries, 4 boxes of 32)
             const uint32_t tm_dq = tmem_base + C::kColDQ;
-            const int g_ds = b % p.ds_groups;
             const bool rpe_skip = kBiasMode == 3 && p.rpe.dconst != nullptr;
+            B200T5_ITEM_BEGIN
+            if (n_iter == 0) continue;
+            const int g_ds = b % p.ds_groups;
             for (int k = 0; k < n_iter; ++k) {
+                const int kg = kb + k;                                  // tile count over the whole CTA
                 // second arrival for the boxes of the previous tile: its TMA group (committed a moment ago) has read them.  Done
                 // first thing, so that the boxes are free again one whole tile before their next use.
-                if (k > 0 && leader) {
+                if (kg > 0 && leader) {
                     bulk_wait_group_read<0>();
-                    mbar_arrive(box_free + ((k - 1) & 1));
+                    mbar_arrive(box_free + ((kg - 1) & 1));
                 }
                 __syncwarp();
                 for (int j = 0; j < kNSub; ++j) {
-                    mbar_wait(pds_full + (k & 1) * kNSub + j, (k >> 1) & 1);
+                    mbar_wait(pds_full + (kg & 1) * kNSub + j, (kg >> 1) & 1);
                     if (kBiasMode != 0 && leader) {
                         const int m0 = (i_start + k) * kBM + j * kSub;
                         bool skip = false;
@@ -444,18 +503,18 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
                         skip = true;
 #endif
                         if (!skip) {
-                            const uint8_t* box = smem + C::kDS + ((k & 1) * kNSub + j) * kBoxBytes;
+                            const uint8_t* box = smem + C::kDS + ((kg & 1) * kNSub + j) * kBoxBytes;
                             if (p.ds_use_reduce) tma_reduce_add_4d(&p.map_ds, box, m0, col0, h, g_ds);
                             else tma_store_4d(&p.map_ds, box, m0, col0, h, g_ds);
                         }
                     }
                 }
                 if (leader) bulk_commit_group();                    // one group per tile (possibly empty)
-                if (k == 0) mbar_wait(k_full, 0);
-                else mbar_wait(dq_empty, (k - 1) & 1);             // dQ(k-1) has been drained out of TMEM
+                if (k == 0) mbar_wait(k_full, it & 1);             // K of this item is in shared memory
+                if (kg > 0) mbar_wait(dq_empty, (kg - 1) & 1);     // the previous dQ tile has been drained out of TMEM
                 tc_fence_after();
                 if (lane == 0) BWD3_TS(4, 4 * k + 3, 2);
-                const uint32_t ds_mn_lo = ds_mn_lo0 + (k & 1) * ((kNSub * kBoxBytes) >> 4);
+                const uint32_t ds_mn_lo = ds_mn_lo0 + (kg & 1) * ((kNSub * kBoxBytes) >> 4);
                 if (leader) {
                     // dQ_tile = dS K   (K dimension = the 128 keys of this CTA; A = dS^T boxes read MN-major)
 #pragma unroll
@@ -463,11 +522,12 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
                         umma_ss2(tm_dq, ds_mn_lo + kk * ((16 * 64) >> 4), hi_ds, k_mn_lo + ((kk * 16 * C::kRowBytes) >> 4), hi_op,
                                  idesc_dq, kk > 0 ? 1u : 0u);
                     umma_commit(dq_full);
-                    umma_commit(box_free + (k & 1));                // first of the two arrivals: the MMAs have read the boxes
+                    umma_commit(box_free + (kg & 1));               // first of the two arrivals: the MMAs have read the boxes
                     if (k == n_iter - 1) umma_commit(all_done);
                 }
                 __syncwarp();
             }
+            B200T5_ITEM_END
             if (leader) bulk_wait_group_read<0>();                  // shared memory must outlive the reads; the writes complete by themselves
         }
     } else if (warp >= kWarpDrain0) {
@@ -475,35 +535,14 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
         setmaxnreg_dec<56>();
         const int r = (warp & 3) * 32 + lane;                 // TMEM lane
         const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
-        if (n_iter > 0) {
-            // ---- prologue: K and V rows of this key block, shared memory (TMA, swizzled rows) -> TMEM (the A operands of
-            //      S^T and dP^T).  Reading them from global memory here cost ~4 000 cycles per CTA (56 registers: the loads
-            //      of a row went out in small batches, each one a trip to HBM) ----
-            mbar_wait(k_full, 0);
-            const int sw = kD == 64 ? (r & 7) : (kD == 32 ? ((r >> 1) & 3) : ((r >> 2) & 1));   // 16-byte chunk ^= f(row)
-#pragma unroll
-            for (int which = 0; which < 2; ++which) {
-                const uint8_t* row = smem + (which == 0 ? C::kK : C::kDQ) + r * C::kRowBytes;
-                const uint32_t tm_dst = tmem_base + lane_off + (which == 0 ? C::kColKt : C::kColVt);
-#pragma unroll
-                for (int i = 0; i < kD / 16; ++i) {                    // 8 words (16 elements) at a time
-                    const uint4 a = *reinterpret_cast<const uint4*>(row + (((2 * i) ^ sw) << 4));
-                    const uint4 c = *reinterpret_cast<const uint4*>(row + (((2 * i + 1) ^ sw) << 4));
-                    const uint32_t w[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
-                    tmem_st8(tm_dst + 8 * i, w);
-                }
-            }
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(kt_ready);
-        }
         const uint32_t tm_dq = tmem_base + lane_off + C::kColDQ;
-        const int dq_c3 = (nb % p.dq_groups) * p.B + b;       // (group, batch) slice of the dQ surface
         uint8_t* stage_row = smem + C::kDQ + r * (kD * 2);
+        B200T5_ITEM_BEGIN
+        if (n_iter == 0) continue;
+        const int dq_c3 = (nb % p.dq_groups) * p.B + b;       // (group, batch) slice of the dQ surface
         for (int k = 0; k < n_iter; ++k) {
             if (r == 0) BWD3_TS(5, k, 0);
-            mbar_wait(dq_full, k & 1);
+            mbar_wait(dq_full, (kb + k) & 1);
             tc_fence_after();
             if (r == 0) BWD3_TS(5, k, 1);
             // (56 registers per thread here: 16 columns at a time, keep only the packed words)
@@ -521,6 +560,7 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
             if (lane == 0) mbar_arrive(dq_empty);             // the dQ columns may be overwritten by tile k + 1
             if (r == 0) bulk_wait_group_read<0>();            // staging tile: the previous reduce has read it
             named_bar_sync(5, 128);
+            if (r == 0) BWD3_TS(5, k, 3);
 #pragma unroll
             for (int i = 0; i < kD; i += 8) {
                 const int c16 = i / 8;
@@ -537,14 +577,13 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
             }
             if (r == 0) BWD3_TS(5, k, 2);
         }
-        if (r == 0) bulk_wait_group_read<0>();
+        B200T5_ITEM_END
+        if (r == 0) bulk_wait_group_read<0>();                // shared memory must outlive the reads
     } else {
         // =============================== compute warpgroups 0..3 (warps 0..15) ===============================
         setmaxnreg_inc<96>();     // the CTA owns 896 x 72 = 64 512 registers (its launch allocation): 512 x 96 + 128 x 56 (drain) + 256 x 32 (control)
         const int wg = warp >> 2;                             // == j: the sub-tile of every tile / the buffer this warpgroup owns
         const int r = (warp & 3) * 32 + lane;                 // key row in the block == TMEM lane
-        const int gn = col0 + r;                              // global key index
-        const bool key_ok = gn < p.N;
         const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
         const uint32_t tm_s = tmem_base + lane_off + C::kColS + (wg & 1) * kSub;      // sub-tile t = 4k + wg uses buffer t & 1
         const uint32_t tm_dp = tmem_base + lane_off + C::kColDP + (wg & 1) * kSub;
@@ -554,13 +593,26 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
         const float scale_log2 = p.sm_scale * kLog2e;
 
         const float* band = reinterpret_cast<const float*>(smem + C::kBand);   // [bias mode 3]
-        if (kBiasMode == 3) {
+        int band_head = -1;
+        const bool rpe_skip = kBiasMode == 3 && p.rpe.dconst != nullptr;
+        // The 64 bytes of bias this thread needs for its next sub-tile are copied global -> shared with cp.async (no registers:
+        // they would be live across a whole sub-tile) into the band's shared memory (mode 3 is the other user): [wg][chunk][row].
+        uint4* const bias_stage = reinterpret_cast<uint4*>(smem + C::kBand) + wg * (4 * 128) + r;
+
+        B200T5_ITEM_BEGIN
+#ifdef B200T5_BWD_TIMING
+        if (threadIdx.x == 0 && blockIdx.x < 8 && it < 19) g_bwd3_item_ts[blockIdx.x][it] = clock64();
+#endif
+        const int gn = col0 + r;                              // global key index
+        const bool key_ok = gn < p.N;
+        if (kBiasMode == 3 && n_iter > 0 && h != band_head) {
+            // (every compute warp left the previous item through the barrier at its end: nobody reads the old band any more)
             float* dst = reinterpret_cast<float*>(smem + C::kBand);
             const float* src = p.rpe.band + (int64_t)h * p.rpe.band_len;
             for (int i = threadIdx.x; i < p.rpe.band_len; i += 512) dst[i] = __ldg(src + i);
             named_bar_sync(6, 512);
+            band_head = h;
         }
-        const bool rpe_skip = kBiasMode == 3 && p.rpe.dconst != nullptr;
         float ds_const_lo = 0.f, ds_const_hi = 0.f;
 
         // dense bias: repacked copy [bh][key block][32-query block][4][128 keys][8 queries] (16-bit)
@@ -571,9 +623,6 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
             const int64_t n_mb = kNSub * p.num_m_blocks;              // the copy covers whole 128-query tiles
             bias_blk = reinterpret_cast<const uint4*>(p.bias) + ((bh * nnb + nb) * n_mb) * (4 * 128) + r;
         }
-        // The 64 bytes of bias this thread needs for its next sub-tile are copied global -> shared with cp.async (no registers:
-        // they would be live across a whole sub-tile) into the band's shared memory (mode 3 is the other user): [wg][chunk][row].
-        uint4* const bias_stage = reinterpret_cast<uint4*>(smem + C::kBand) + wg * (4 * 128) + r;
         auto load_bias = [&](int kk) {                          // kk: tile (iteration) whose bias is fetched
             const uint4* src = bias_blk + (int64_t)(((i_start + kk) * kBM + wg * kSub) / kSub) * (4 * 128);
 #pragma unroll
@@ -586,11 +635,43 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
             const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
             for (int c = 0; c < 2 * kD; c += 8) tmem_st8(tmem_base + lane_off + C::kColDV + c, z);
+            // ---- item prologue: K and V rows of this key block, shared memory (TMA, swizzled rows) -> TMEM (the A operands of
+            //      S^T and dP^T).  This warpgroup is idle here anyway (its first S^T cannot exist before K is in TMEM), has passed
+            //      all_done of the previous item in its epilogue (the TMEM copies are free) and, unlike the drain warpgroup, is
+            //      not busy with the previous item's last dQ.  (From global memory straight to TMEM this cost ~4 000 cycles.) ----
+            const int pv = 2 * kb + it, sv = pv % C::kSlots;            // ring position of this item's V tile
+            mbar_wait(k_full, it & 1);
+            mbar_wait(qdo_full + sv, (pv / C::kSlots) & 1);
+            const int sw = kD == 64 ? (r & 7) : (kD == 32 ? ((r >> 1) & 3) : ((r >> 2) & 1));   // 16-byte chunk ^= f(row)
+#pragma unroll
+            for (int which = 0; which < 2; ++which) {
+                const uint8_t* row = which == 0 ? smem + C::kK + r * C::kRowBytes
+                                                : smem + (r < C::kSlotRows ? C::kQ : C::kDO) + sv * C::kSlotBytes + (r & (C::kSlotRows - 1)) * C::kRowBytes;
+                const uint32_t tm_dst = tmem_base + lane_off + (which == 0 ? C::kColKt : C::kColVt);
+#pragma unroll
+                for (int i = 0; i < kD / 16; ++i) {                    // 8 words (16 elements) at a time
+                    const uint4 a = *reinterpret_cast<const uint4*>(row + (((2 * i) ^ sw) << 4));
+                    const uint4 c = *reinterpret_cast<const uint4*>(row + (((2 * i + 1) ^ sw) << 4));
+                    const uint32_t w[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+                    tmem_st8(tm_dst + 8 * i, w);
+                }
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            fence_proxy_async_smem();                                  // the slot goes back to the TMA producer
+            __syncwarp();
+            if (lane == 0) mbar_arrive(kt_ready);
+            named_bar_sync(7, 128);                                    // every row of V has been read
+            if (r == 0) {
+                mbar_arrive(qdo_empty + sv);
+                mbar_arrive(qdo_empty + sv);
+            }
         }
 
         for (int k = 0; k < n_iter; ++k) {
+            const int kg = kb + k;                            // tile count over the whole CTA: every barrier parity follows from it
             const int m0 = (i_start + k) * kBM + wg * kSub;
-            uint8_t* const sDS = smem + C::kDS + ((k & 1) * kNSub + wg) * kBoxBytes + r * 64;
+            uint8_t* const sDS = smem + C::kDS + ((kg & 1) * kNSub + wg) * kBoxBytes + r * 64;
 
             // masks: key tail (whole row) and causal (query m sees key n iff n <= m + pseq, i.e. c >= gn - pseq - m0)
             const bool need_mask = (col0 + kBN > p.N) || (kCausal && (col0 + kBN - 1 - pseq > m0));
@@ -610,7 +691,7 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
             }
 
             if (r == 0) BWD3_TS(wg, k, 0);
-            mbar_wait(sdp_full + wg, k & 1);
+            mbar_wait(sdp_full + wg, kg & 1);
             tc_fence_after();
             if (r == 0) BWD3_TS(wg, k, 1);
 
@@ -636,7 +717,7 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
                 }
                 const uint32_t(&dr)[16] = *reinterpret_cast<const uint32_t(*)[16]>(drr + hc * 16);
                 // statistics of the slot: the S^T MMAs of this sub-tile were issued after warp A saw the slot's barrier complete
-                const float* nl = reinterpret_cast<const float*>(smem + C::kStats) + (((4 * k + wg) >> 1) % C::kSlots) * (2 * C::kSlotRows) + (wg & 1) * kSub + hc * 16;
+                const float* nl = reinterpret_cast<const float*>(smem + C::kStats) + ((((4 * kg + wg) >> 1) + it + 1) % C::kSlots) * (2 * C::kSlotRows) + (wg & 1) * kSub + hc * 16;
                 const float* nd = nl + C::kSlotRows;
                 // bias mode 3, element c of this half: band[(gn - (m0 + 16 hc + c)) - band_lo]
                 const float* bp = band + (gn - m0 - hc * 16 - p.rpe.band_lo);
@@ -658,10 +739,10 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
                     else v3_chunk<kBf16, kBiasMode, false, false, false>(srh, dr, nl, nd, bw, bp, 0.f, scale_log2, 0, pp, dd, dummy);
                 }
                 if (r == 0) BWD3_TS(wg, k, 5 + hc);                  // (5: first half computed, 6: second half computed)
-                if (hc == 0 && k > 0) {
-                    mbar_wait(pds_free + wg, (k - 1) & 1);        // dV,dK of this warpgroup's previous sub-tile have read P^T / dS^T
+                if (hc == 0 && kg > 0) {
+                    mbar_wait(pds_free + wg, (kg - 1) & 1);       // dV,dK of this warpgroup's previous sub-tile have read P^T / dS^T
                     // the dS^T box (tile parity, j) was last used two tiles ago: its dQ MMAs and its TMA reduce have read it
-                    if (k >= 2) mbar_wait(box_free + (k & 1), ((k >> 1) - 1) & 1);
+                    if (kg >= 2) mbar_wait(box_free + (kg & 1), ((kg >> 1) - 1) & 1);
                     tc_fence_after();
                 }
                 if (r == 0 && hc == 0) BWD3_TS(wg, k, 7);             // (7: P^T / dS^T buffers and the box are free)
@@ -674,7 +755,7 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
             tmem_st_wait();
             tc_fence_before();
             fence_proxy_async_smem();
-            mbar_arrive(pds_full + (k & 1) * kNSub + wg);
+            mbar_arrive(pds_full + (kg & 1) * kNSub + wg);
             if (r == 0) BWD3_TS(wg, k, 3);
             if (kBiasMode == 1 && k + 1 < n_iter) load_bias(k + 1);       // lands during the wait for the next S^T
         }
@@ -700,9 +781,9 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
                 : reinterpret_cast<uint8_t*>(p.dk) + 2 * ((int64_t)b * p.dk_sb + (int64_t)h * p.dk_sh + (int64_t)gn * p.dk_sn);
             const float sc = is_dv ? 1.f : p.sm_scale;
             if (n_iter > 0) {
-                // every MMA of warp B -- the last writers of dV / dK -- completed.  (A dedicated single-phase barrier: the compute
-                // warps no longer follow dq_full tile by tile, so its parity alone could match a phase two tiles old.)
-                mbar_wait(all_done, 0);
+                // every MMA of this item completed -- warp B's are the last writers of dV / dK.  (A dedicated barrier, one phase
+                // per item: the compute warps do not follow dq_full tile by tile, whose parity could match a phase two tiles old.)
+                mbar_wait(all_done, it & 1);
                 tc_fence_after();
                 const uint32_t tm_acc = tmem_base + lane_off + (is_dv ? C::kColDV : C::kColDK) + c_first;
                 // (all of the warpgroup's columns with one load + one wait, then the stores: kColsPer = 8, 16 or 32)
@@ -728,12 +809,22 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
                     }
                 }
                 tc_fence_before();
+                // every compute warp has read dV / dK (and the band): warpgroup 0 may zero the accumulators for the next item
+                named_bar_sync(6, 512);
+                tc_fence_after();
             } else if (key_ok) {
 #pragma unroll
                 for (int c = 0; c < kColsPer; c += 8) *reinterpret_cast<uint4*>(out_row + 2 * (c_first + c)) = make_uint4(0, 0, 0, 0);
             }
         }
+        if (n_iter == 0) continue;                            // (an item no query sees: nothing was counted)
+        B200T5_ITEM_END
+#ifdef B200T5_BWD_TIMING
+        if (threadIdx.x == 0 && blockIdx.x < 8 && it < 20) g_bwd3_item_ts[blockIdx.x][it] = clock64();
+#endif
     }
+#undef B200T5_ITEM_BEGIN
+#undef B200T5_ITEM_END
 
     __syncthreads();
     if (warp == kWarpMmaA) {
@@ -751,7 +842,18 @@ static cudaError_t launch_bwd3_inst(const AttnBwdKernelParams& kp, cudaStream_t 
     auto kern = attn_bwd_kernel_v3<kD, kBf16, kBiasMode, kCausal>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal);
     if (e != cudaSuccess) return e;
-    const int grid = kp.B * kp.H * kp.num_n_blocks;
+    // persistent: one CTA per SM walks the work items (batch, head, key block) round-robin
+    static int sm_count[64] = {0};
+    int dev = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (sm_count[dev] == 0) {
+        int n = 0;
+        if ((e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+        sm_count[dev] = n;
+    }
+    const long long n_items = (long long)kp.B * kp.H * kp.num_n_blocks;
+    const int grid = static_cast<int>(n_items < sm_count[dev] ? n_items : sm_count[dev]);
     kern<<<grid, kThreads, C::kTotal, stream>>>(kp);
     count_launch();
 #ifdef B200T5_BWD_TIMING
@@ -761,7 +863,7 @@ static cudaError_t launch_bwd3_inst(const AttnBwdKernelParams& kp, cudaStream_t 
         cudaMemcpyFromSymbol(ts, g_bwd3_ts, sizeof(ts));
         const long long t0 = ts[0][0][0];
         const char* names[8] = {"wg0 [wait S, S ready, math done, stored + signalled | S in registers, half 0 computed, half 1 computed, buffers free]  (per tile)", "wg1", "wg2", "wg3",
-                                "mma B [wait P/dS(t), ready, dq gate (warp C), issued]  (per sub-tile)", "drain [wait dQ, dQ ready, reduce issued]  (per tile)",
+                                "mma B [wait P/dS(t), ready, dq gate (warp C), issued]  (per sub-tile)", "drain [wait dQ, dQ ready, reduce issued, staging free]  (per tile)",
                                 "mma A [wait Q/dO slot, slot ready, buffers free, issued]  (per sub-tile)", "producer [wait slot empty, empty]  (per sub-tile)"};
         for (int role = 0; role < 8; ++role) {
             printf("BWD3_TIMING %s\n", names[role]);
@@ -770,6 +872,13 @@ static cudaError_t launch_bwd3_inst(const AttnBwdKernelParams& kp, cudaStream_t 
                 for (int j = 0; j < (role < 4 ? 8 : 4); ++j) printf(" %7lld", ts[role][k][j] ? ts[role][k][j] - t0 : 0);
                 printf("\n");
             }
+        }
+        static long long its[8][20];
+        cudaMemcpyFromSymbol(its, g_bwd3_item_ts, sizeof(its));
+        for (int c = 0; c < 8; ++c) {
+            printf("BWD3_ITEMS cta %d: cycles per item:", c);
+            for (int i = 0; i + 1 < 20 && its[c][i + 1] > its[c][i] && its[c][i] > 0; ++i) printf(" %lld", its[c][i + 1] - its[c][i]);
+            printf("\n");
         }
         fflush(stdout);
     }
