@@ -82,18 +82,18 @@ struct Bwd3Cfg {
     // two whole tiles left the first sub-tile of every other tile waiting ~2 400 cycles for its TMA; a ring of eleven 32-row
     // slots made the single producer lane the pacemaker of the whole CTA: 4 operations + a probe = ~650 cycles per sub-tile,
     // 2 600 per tile against 1 500 of math -- profiles/r2c_bwd_v3_timeline_*.)
-    static constexpr int kSlots = kBiasMode == 0 ? 7 : 5;
+    static constexpr int kSlots = kBiasMode == 0 ? 6 : 4;
     static constexpr int kSlotRows = 2 * kSub;
     static constexpr int kSlotBytes = 2 * kSubTileBytes;
     static constexpr int kK = 0;
-    static constexpr int kQ = kK + kTileBytes;
+    static constexpr int kQ = kK + 2 * kTileBytes;                     // K is double-buffered over the work items of the CTA
     static constexpr int kDO = kQ + kSlots * kSlotBytes;
     static constexpr int kDS = kDO + kSlots * kSlotBytes;              // [2 tiles][4 boxes] dS^T
     static constexpr int kDQ = kDS + 2 * kNSub * kBoxBytes;            // dQ staging tile [128][D] io dtype (prologue: the V tile)
     static constexpr int kBand = kDQ + kTileBytes;                     // relative-position band (mode 3) / bias staging (mode 1), 32 KB
     static constexpr int kStats = kBand + (kBiasMode == 0 ? 0 : 32768);                     // [kSlots][2][64] fp32: -L*log2e, -delta of the slot's queries
     static constexpr int kBars = kStats + kSlots * 2 * kSlotRows * 4;
-    static constexpr int kNumBars = 2 + 2 * kSlots + 5 * kNSub + 3 + 2 + 2;
+    static constexpr int kNumBars = 2 + 2 * kSlots + 5 * kNSub + 3 + 2 + 2 + 1;
     static constexpr int kTmemSlot = kBars + kNumBars * 8;
     static constexpr int kTotal = kTmemSlot + 16;
     static_assert(kTotal <= 232448, "shared memory budget");
@@ -257,6 +257,15 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
         ++it;                                                                                                               \
     }
     const Item first_item = decode(blockIdx.x);
+    auto next_item = [&](int item) {                                  // the next item of this CTA that has work (n_iter == 0: none)
+        Item wn;
+        wn.n_iter = 0;
+        for (int nxt = item + static_cast<int>(gridDim.x); nxt < n_items; nxt += gridDim.x) {
+            wn = decode(nxt);
+            if (wn.n_iter > 0) break;
+        }
+        return wn;
+    };
 
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kBars);
     uint64_t* k_full = bars;
@@ -276,6 +285,7 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
     uint64_t* dq_empty = dq_full + 1;
     uint64_t* all_done = dq_empty + 1;                  // every MMA of the CTA completed (single phase: the epilogue's gate; B and C commit)
     uint64_t* b_turn = all_done + 3;                    // [2] B0 <-> B1 token: the dV / dK MMAs are issued in sub-tile order (bitwise reproducible sums)
+    uint64_t* sdp_done = all_done + 5;                  // every S^T / dP^T MMA of the item completed (four A warps commit; warpgroup 0 waits)
     uint64_t* box_free = all_done + 1;                  // [2] dS^T boxes of tile parity: dQ MMAs done + TMA reduce reads done (C -> compute)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::kTmemSlot);
 
@@ -312,6 +322,7 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
         mbar_init(box_free + 1, 2);
         mbar_init(b_turn + 0, 1);
         mbar_init(b_turn + 1, 1);
+        mbar_init(sdp_done, 4);
         for (int i = 0; i < kNSub; ++i) {
             mbar_init(sdp_full + i, 1);
             mbar_init(pds_full + i, 128);                 // every thread of compute warpgroup i arrives by itself
@@ -344,26 +355,16 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
             // ---- per item: K, V (the first item's were requested before the setup barrier); then the Q / dO ring ----
             B200T5_ITEM_BEGIN
             if (n_iter == 0) continue;
-            // Ring positions: item `it` takes position 2 kb + it for its V tile and 2 kb + it + 1 + u for its half tile u.
-            if (!(it == 0 && item == static_cast<int>(blockIdx.x))) {
-                // V: as soon as a ring slot is free (well before the item boundary); it waits there until warpgroup 0 copies it
-                // into TMEM.  K: its shared-memory tile is free once every dQ MMA of the previous item completed.
-                const int pv = 2 * kb + it, sv = pv % C::kSlots;
-                mbar_wait_producer(qdo_empty + sv, ((pv / C::kSlots) & 1) ^ 1);
-                mbar_arrive_expect_tx(qdo_full + sv, 2 * C::kSlotBytes);
-                tma_load_4d(smem + C::kQ + sv * C::kSlotBytes, &p.map_v, qdo_full + sv, 0, col0, h, b);
-                tma_load_4d(smem + C::kDO + sv * C::kSlotBytes, &p.map_v, qdo_full + sv, 0, col0 + C::kSlotRows, h, b);
+            // Ring positions: item `it` takes position 2 kb + it for its V tile and 2 kb + it + 1 + u for its half tile u.  K and V
+            // of an item are requested right after the last half tile of the item before it (below), so that warpgroup 0 can put
+            // them into TMEM while that item is still finishing; only the CTA's first item asks for them here (if the setup code
+            // above has not already).
+            if (it == 0 && item != static_cast<int>(blockIdx.x)) {
+                mbar_arrive_expect_tx(qdo_full + 0, 2 * C::kSlotBytes);
+                tma_load_4d(smem + C::kQ, &p.map_v, qdo_full + 0, 0, col0, h, b);
+                tma_load_4d(smem + C::kDO, &p.map_v, qdo_full + 0, 0, col0 + C::kSlotRows, h, b);
                 mbar_arrive_expect_tx(k_full, C::kTileBytes);
-                if (it > 0) mbar_wait(all_done, (it - 1) & 1);
                 tma_load_4d(smem + C::kK, &p.map_k, k_full, 0, col0, h, b);
-            }
-            // K of the next item: into L2 now, so that its TMA load at the item boundary (which is on the critical path: the tile
-            // can only land once this item's dQ MMAs are done with K) starts from L2 instead of HBM.  (V is loaded early.)
-            for (int nxt = item + static_cast<int>(gridDim.x); nxt < n_items; nxt += gridDim.x) {
-                const Item wn = decode(nxt);
-                if (wn.n_iter == 0) continue;
-                tma_prefetch_l2_4d(&p.map_k, 0, wn.col0, wn.h, wn.b);
-                break;
             }
             const float* stat_bh = p.nl + ((int64_t)b * p.H + h) * (2 * (int64_t)p.m_pad);
             for (int u = 0; u < 2 * n_iter; ++u) {
@@ -379,6 +380,21 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
                 // row statistics of the 64 queries: [-L * log2e | -delta], one 512-byte record per 64 padded rows
                 bulk_load_1d(reinterpret_cast<float*>(smem + C::kStats) + s * (2 * C::kSlotRows), stat_bh + (m0 / C::kSlotRows) * (2 * C::kSlotRows),
                              2 * C::kSlotRows * 4, qdo_full + s);
+            }
+            {
+                // ---- K and V of the CTA's next item.  V: the ring position after this item's last half tile (as soon as a slot
+                //      is free).  K: the other shared-memory buffer, free since every dQ MMA of the item BEFORE this one completed.
+                const Item wn = next_item(item);
+                if (wn.n_iter > 0) {
+                    const int pv = 2 * (kb + n_iter) + it + 1, sv = pv % C::kSlots;
+                    mbar_wait_producer(qdo_empty + sv, ((pv / C::kSlots) & 1) ^ 1);
+                    mbar_arrive_expect_tx(qdo_full + sv, 2 * C::kSlotBytes);
+                    tma_load_4d(smem + C::kQ + sv * C::kSlotBytes, &p.map_v, qdo_full + sv, 0, wn.col0, wn.h, wn.b);
+                    tma_load_4d(smem + C::kDO + sv * C::kSlotBytes, &p.map_v, qdo_full + sv, 0, wn.col0 + C::kSlotRows, wn.h, wn.b);
+                    if (it > 0) mbar_wait(all_done, (it - 1) & 1);
+                    mbar_arrive_expect_tx(k_full, C::kTileBytes);
+                    tma_load_4d(smem + C::kK + ((it + 1) & 1) * C::kTileBytes, &p.map_k, k_full, 0, wn.col0, wn.h, wn.b);
+                }
             }
             B200T5_ITEM_END
         } else if (warp == kWarpMmaA || warp == kWarpMmaA1 || warp == kWarpMmaA2 || warp == kWarpMmaA3) {
@@ -420,6 +436,7 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
                     for (int kk = 0; kk < kD / 16; ++kk)
                         umma_ts2(tm_dp, tm_vt + kk * 8, do_lo0 + so + kk * 2, hi_op, idesc_s, kk > 0 ? 1u : 0u);
                     umma_commit(sdp_full + j);
+                    if (t + kNSub >= T) umma_commit(sdp_done);      // this warp's last sub-tile of the item: K, V in TMEM are done with
                 }
                 __syncwarp();
                 if (lane == 0) BWD3_TS(6, t, 3);
@@ -510,7 +527,9 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
                     }
                 }
                 if (leader) bulk_commit_group();                    // one group per tile (possibly empty)
-                if (k == 0) mbar_wait(k_full, it & 1);             // K of this item is in shared memory
+                // (K of this item is in shared memory: warpgroup 0 copied it into TMEM before the first S^T of the item could be
+                //  issued, and this tile's dS^T exists.  No wait on k_full here: with short items the NEXT item's K may already
+                //  have completed a further phase of that barrier, and a parity probe cannot tell phases two apart.)
                 if (kg > 0) mbar_wait(dq_empty, (kg - 1) & 1);     // the previous dQ tile has been drained out of TMEM
                 tc_fence_after();
                 if (lane == 0) BWD3_TS(4, 4 * k + 3, 2);
@@ -519,7 +538,7 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
                     // dQ_tile = dS K   (K dimension = the 128 keys of this CTA; A = dS^T boxes read MN-major)
 #pragma unroll
                     for (int kk = 0; kk < kBN / 16; ++kk)
-                        umma_ss2(tm_dq, ds_mn_lo + kk * ((16 * 64) >> 4), hi_ds, k_mn_lo + ((kk * 16 * C::kRowBytes) >> 4), hi_op,
+                        umma_ss2(tm_dq, ds_mn_lo + kk * ((16 * 64) >> 4), hi_ds, k_mn_lo + (it & 1) * (C::kTileBytes >> 4) + ((kk * 16 * C::kRowBytes) >> 4), hi_op,
                                  idesc_dq, kk > 0 ? 1u : 0u);
                     umma_commit(dq_full);
                     umma_commit(box_free + (kg & 1));               // first of the two arrivals: the MMAs have read the boxes
@@ -599,6 +618,39 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
         // they would be live across a whole sub-tile) into the band's shared memory (mode 3 is the other user): [wg][chunk][row].
         uint4* const bias_stage = reinterpret_cast<uint4*>(smem + C::kBand) + wg * (4 * 128) + r;
 
+        // K and V rows of a key block, shared memory (TMA, swizzled rows) -> TMEM (the A operands of S^T and dP^T); warpgroup 0.
+        // `item_no` = the (non-empty) item they belong to: K sits in buffer item_no & 1 (k_full phase item_no), V in the ring
+        // slot of position `pv`.  (From global memory straight to TMEM this cost ~4 000 cycles per item.)
+        auto kv_to_tmem = [&](int item_no, int pv) {
+            const int sv = pv % C::kSlots;
+            mbar_wait(k_full, item_no & 1);
+            mbar_wait(qdo_full + sv, (pv / C::kSlots) & 1);
+            const int sw = kD == 64 ? (r & 7) : (kD == 32 ? ((r >> 1) & 3) : ((r >> 2) & 1));   // 16-byte chunk ^= f(row)
+#pragma unroll
+            for (int which = 0; which < 2; ++which) {
+                const uint8_t* row = which == 0 ? smem + C::kK + (item_no & 1) * C::kTileBytes + r * C::kRowBytes
+                                                : smem + (r < C::kSlotRows ? C::kQ : C::kDO) + sv * C::kSlotBytes + (r & (C::kSlotRows - 1)) * C::kRowBytes;
+                const uint32_t tm_dst = tmem_base + lane_off + (which == 0 ? C::kColKt : C::kColVt);
+#pragma unroll
+                for (int i = 0; i < kD / 16; ++i) {                    // 8 words (16 elements) at a time
+                    const uint4 a = *reinterpret_cast<const uint4*>(row + (((2 * i) ^ sw) << 4));
+                    const uint4 c = *reinterpret_cast<const uint4*>(row + (((2 * i + 1) ^ sw) << 4));
+                    const uint32_t w[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+                    tmem_st8(tm_dst + 8 * i, w);
+                }
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            fence_proxy_async_smem();                                  // the slot goes back to the TMA producer
+            __syncwarp();
+            if (lane == 0) mbar_arrive(kt_ready);
+            named_bar_sync(7, 128);                                    // every row of V has been read
+            if (r == 0) {
+                mbar_arrive(qdo_empty + sv);
+                mbar_arrive(qdo_empty + sv);
+            }
+        };
+
         B200T5_ITEM_BEGIN
 #ifdef B200T5_BWD_TIMING
         if (threadIdx.x == 0 && blockIdx.x < 8 && it < 19) g_bwd3_item_ts[blockIdx.x][it] = clock64();
@@ -635,37 +687,8 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
             const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
             for (int c = 0; c < 2 * kD; c += 8) tmem_st8(tmem_base + lane_off + C::kColDV + c, z);
-            // ---- item prologue: K and V rows of this key block, shared memory (TMA, swizzled rows) -> TMEM (the A operands of
-            //      S^T and dP^T).  This warpgroup is idle here anyway (its first S^T cannot exist before K is in TMEM), has passed
-            //      all_done of the previous item in its epilogue (the TMEM copies are free) and, unlike the drain warpgroup, is
-            //      not busy with the previous item's last dQ.  (From global memory straight to TMEM this cost ~4 000 cycles.) ----
-            const int pv = 2 * kb + it, sv = pv % C::kSlots;            // ring position of this item's V tile
-            mbar_wait(k_full, it & 1);
-            mbar_wait(qdo_full + sv, (pv / C::kSlots) & 1);
-            const int sw = kD == 64 ? (r & 7) : (kD == 32 ? ((r >> 1) & 3) : ((r >> 2) & 1));   // 16-byte chunk ^= f(row)
-#pragma unroll
-            for (int which = 0; which < 2; ++which) {
-                const uint8_t* row = which == 0 ? smem + C::kK + r * C::kRowBytes
-                                                : smem + (r < C::kSlotRows ? C::kQ : C::kDO) + sv * C::kSlotBytes + (r & (C::kSlotRows - 1)) * C::kRowBytes;
-                const uint32_t tm_dst = tmem_base + lane_off + (which == 0 ? C::kColKt : C::kColVt);
-#pragma unroll
-                for (int i = 0; i < kD / 16; ++i) {                    // 8 words (16 elements) at a time
-                    const uint4 a = *reinterpret_cast<const uint4*>(row + (((2 * i) ^ sw) << 4));
-                    const uint4 c = *reinterpret_cast<const uint4*>(row + (((2 * i + 1) ^ sw) << 4));
-                    const uint32_t w[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
-                    tmem_st8(tm_dst + 8 * i, w);
-                }
-            }
-            tmem_st_wait();
-            tc_fence_before();
-            fence_proxy_async_smem();                                  // the slot goes back to the TMA producer
-            __syncwarp();
-            if (lane == 0) mbar_arrive(kt_ready);
-            named_bar_sync(7, 128);                                    // every row of V has been read
-            if (r == 0) {
-                mbar_arrive(qdo_empty + sv);
-                mbar_arrive(qdo_empty + sv);
-            }
+            // (the CTA's first item: K, V -> TMEM here; later items: at the end of the item before, see below)
+            if (it == 0) kv_to_tmem(0, 0);
         }
 
         for (int k = 0; k < n_iter; ++k) {
@@ -759,6 +782,18 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
             if (r == 0) BWD3_TS(wg, k, 3);
             if (kBiasMode == 1 && k + 1 < n_iter) load_bias(k + 1);       // lands during the wait for the next S^T
         }
+        if (r == 0) BWD3_TS(wg, 8, 0);                        // (row 8 of the timeline: the item boundary)
+        if (wg == 0 && n_iter > 0 && next_item(item).n_iter > 0) {
+            // ---- K, V of the CTA's next item -> TMEM, while the other warpgroups, the dV / dK / dQ MMAs and the dQ drain of this
+            //      item are still at work: the S^T / dP^T MMAs of the next item then start at once (the ring runs on).  The TMEM
+            //      copies of K and V are free as soon as the LAST S^T / dP^T MMAs of this item completed (sdp_done).
+            // (A barrier of its own, one phase per item, committed by the four A warps after their last MMAs of the item: a
+            //  non-consumer cannot wait on sdp_full[j] -- a parity probe cannot tell phase kg_last - 1 from kg_last + 1.)
+            mbar_wait(sdp_done, it & 1);
+            tc_fence_after();
+            kv_to_tmem(it + 1, 2 * (kb + n_iter) + it + 1);
+        }
+        if (r == 0) BWD3_TS(wg, 8, 1);                        // next K, V in TMEM
 
         // ---- tail: constant-tile sums; then dV (warpgroups 0, 1: D/2 columns each) and dK * sm_scale (warpgroups 2, 3) ----
         if (kBiasMode == 3 && rpe_skip) {
@@ -785,6 +820,7 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
                 // per item: the compute warps do not follow dq_full tile by tile, whose parity could match a phase two tiles old.)
                 mbar_wait(all_done, it & 1);
                 tc_fence_after();
+                if (r == 0) BWD3_TS(wg, 8, 2);                // all MMAs of the item done
                 const uint32_t tm_acc = tmem_base + lane_off + (is_dv ? C::kColDV : C::kColDK) + c_first;
                 // (all of the warpgroup's columns with one load + one wait, then the stores: kColsPer = 8, 16 or 32)
                 uint32_t acc[kColsPer];
@@ -810,8 +846,10 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
                 }
                 tc_fence_before();
                 // every compute warp has read dV / dK (and the band): warpgroup 0 may zero the accumulators for the next item
+                if (r == 0) BWD3_TS(wg, 8, 3);                // dK / dV written
                 named_bar_sync(6, 512);
                 tc_fence_after();
+                if (r == 0) BWD3_TS(wg, 8, 4);                // every compute warp through its epilogue
             } else if (key_ok) {
 #pragma unroll
                 for (int c = 0; c < kColsPer; c += 8) *reinterpret_cast<uint4*>(out_row + 2 * (c_first + c)) = make_uint4(0, 0, 0, 0);
@@ -867,7 +905,7 @@ static cudaError_t launch_bwd3_inst(const AttnBwdKernelParams& kp, cudaStream_t 
                                 "mma A [wait Q/dO slot, slot ready, buffers free, issued]  (per sub-tile)", "producer [wait slot empty, empty]  (per sub-tile)"};
         for (int role = 0; role < 8; ++role) {
             printf("BWD3_TIMING %s\n", names[role]);
-            for (int k = 0; k < ((role == 4 || role >= 6) ? 32 : 8); ++k) {
+            for (int k = 0; k < ((role == 4 || role >= 6) ? 32 : (role < 4 ? 9 : 8)); ++k) {
                 printf("  %2d:", k);
                 for (int j = 0; j < (role < 4 ? 8 : 4); ++j) printf(" %7lld", ts[role][k][j] ? ts[role][k][j] - t0 : 0);
                 printf("\n");
