@@ -459,6 +459,12 @@ static int attn_bwd_impl(const b200t5_attn_params* p, const b200t5_rpe_params* r
     if ((rc = make_map_4d(&kp.map_do, p->dout, 2, dt, p->D, p->M, p->H, p->B, p->do_strides[2], p->do_strides[1], p->do_strides[0], boxd, qrows, "dout"))) return rc;
     if ((rc = make_map_4d(&kp.map_dq, dq_ws, 2, dt, p->D, p->M, p->H, (uint64_t)w.dq_groups * p->B, p->D, (int64_t)p->M * p->D, (int64_t)p->H * p->M * p->D, boxd, 128, "dq group surface", true))) return rc;
     kp.dq_groups = w.dq_groups;
+    if (w.transposed && p->D == 64) {
+        // dK / dV leave the v3 kernel through TMA stores of [128 keys][32 columns] boxes staged in shared memory (thread = key row
+        // stores straight to global memory cost one L1 request per 16 bytes: ~2 500 cycles per work item)
+        if ((rc = make_map_4d(&kp.map_dk_st, p->dk, 2, dt, p->D, p->N, p->H, p->B, p->dk_strides[2], p->dk_strides[1], p->dk_strides[0], 32, 128, "dk"))) return rc;
+        if ((rc = make_map_4d(&kp.map_dv_st, p->dv, 2, dt, p->D, p->N, p->H, p->B, p->dv_strides[2], p->dv_strides[1], p->dv_strides[0], 32, 128, "dv"))) return rc;
+    }
     // D <= 64: every dense bias goes through the transposed copy (which also absorbs unaligned rows); D = 128: TMA or pointers
     int mode = rpe ? 3 : (p->bias ? (w.transposed ? 1 : bias_mode_of(p)) : 0);
     float* dconst = nullptr;

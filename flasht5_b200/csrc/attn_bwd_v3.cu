@@ -93,7 +93,7 @@ struct Bwd3Cfg {
     static constexpr int kBand = kDQ + kTileBytes;                     // relative-position band (mode 3) / bias staging (mode 1), 32 KB
     static constexpr int kStats = kBand + (kBiasMode == 0 ? 0 : 32768);                     // [kSlots][2][64] fp32: -L*log2e, -delta of the slot's queries
     static constexpr int kBars = kStats + kSlots * 2 * kSlotRows * 4;
-    static constexpr int kNumBars = 2 + 2 * kSlots + 5 * kNSub + 3 + 2 + 2 + 1;
+    static constexpr int kNumBars = 2 + 2 * kSlots + 5 * kNSub + 3 + 2 + 2 + 1 + 2;
     static constexpr int kTmemSlot = kBars + kNumBars * 8;
     static constexpr int kTotal = kTmemSlot + 16;
     static_assert(kTotal <= 232448, "shared memory budget");
@@ -285,6 +285,7 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
     uint64_t* dq_empty = dq_full + 1;
     uint64_t* all_done = dq_empty + 1;                  // every MMA of the CTA completed (single phase: the epilogue's gate; B and C commit)
     uint64_t* b_turn = all_done + 3;                    // [2] B0 <-> B1 token: the dV / dK MMAs are issued in sub-tile order (bitwise reproducible sums)
+    uint64_t* kbuf_free = all_done + 6;                 // [2] every dQ MMA that reads K buffer i completed (warp C -> producer)
     uint64_t* sdp_done = all_done + 5;                  // every S^T / dP^T MMA of the item completed (four A warps commit; warpgroup 0 waits)
     uint64_t* box_free = all_done + 1;                  // [2] dS^T boxes of tile parity: dQ MMAs done + TMA reduce reads done (C -> compute)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::kTmemSlot);
@@ -323,6 +324,8 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
         mbar_init(b_turn + 0, 1);
         mbar_init(b_turn + 1, 1);
         mbar_init(sdp_done, 4);
+        mbar_init(kbuf_free + 0, 1);
+        mbar_init(kbuf_free + 1, 1);
         for (int i = 0; i < kNSub; ++i) {
             mbar_init(sdp_full + i, 1);
             mbar_init(pds_full + i, 128);                 // every thread of compute warpgroup i arrives by itself
@@ -391,7 +394,10 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
                     mbar_arrive_expect_tx(qdo_full + sv, 2 * C::kSlotBytes);
                     tma_load_4d(smem + C::kQ + sv * C::kSlotBytes, &p.map_v, qdo_full + sv, 0, wn.col0, wn.h, wn.b);
                     tma_load_4d(smem + C::kDO + sv * C::kSlotBytes, &p.map_v, qdo_full + sv, 0, wn.col0 + C::kSlotRows, wn.h, wn.b);
-                    if (it > 0) mbar_wait(all_done, (it - 1) & 1);
+                    // (a barrier per K buffer, not all_done: with short items this lane can be late enough for all_done to have
+                    //  completed TWO further phases, which a parity probe cannot tell from none -- found as a deadlock in the
+                    //  causal full-shape test)
+                    if (it > 0) mbar_wait(kbuf_free + ((it + 1) & 1), ((it - 1) >> 1) & 1);
                     mbar_arrive_expect_tx(k_full, C::kTileBytes);
                     tma_load_4d(smem + C::kK + ((it + 1) & 1) * C::kTileBytes, &p.map_k, k_full, 0, wn.col0, wn.h, wn.b);
                 }
@@ -542,7 +548,10 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
                                  idesc_dq, kk > 0 ? 1u : 0u);
                     umma_commit(dq_full);
                     umma_commit(box_free + (kg & 1));               // first of the two arrivals: the MMAs have read the boxes
-                    if (k == n_iter - 1) umma_commit(all_done);
+                    if (k == n_iter - 1) {
+                        umma_commit(all_done);
+                        umma_commit(kbuf_free + (it & 1));          // the item's K buffer is done with
+                    }
                 }
                 __syncwarp();
             }
@@ -613,6 +622,7 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
 
         const float* band = reinterpret_cast<const float*>(smem + C::kBand);   // [bias mode 3]
         int band_head = -1;
+        bool store_pending = false;                           // this warpgroup's dK / dV TMA store of the previous item may still be reading its box
         const bool rpe_skip = kBiasMode == 3 && p.rpe.dconst != nullptr;
         // The 64 bytes of bias this thread needs for its next sub-tile are copied global -> shared with cp.async (no registers:
         // they would be live across a whole sub-tile) into the band's shared memory (mode 3 is the other user): [wg][chunk][row].
@@ -768,6 +778,12 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
                     if (kg >= 2) mbar_wait(box_free + (kg & 1), ((kg >> 1) - 1) & 1);
                     tc_fence_after();
                 }
+                if (hc == 0 && store_pending) {
+                    // (first tile of an item: the box also staged this warpgroup's dK / dV of the item before)
+                    if (r == 0) bulk_wait_group_read<0>();
+                    named_bar_sync(8 + wg, 128);
+                    store_pending = false;
+                }
                 if (r == 0 && hc == 0) BWD3_TS(wg, k, 7);             // (7: P^T / dS^T buffers and the box are free)
                 tmem_st8(tm_p + hc * 8, pp);
                 tmem_st8(tm_ds + hc * 8, dd);
@@ -832,7 +848,30 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
                                  : "r"(tm_acc)
                                  : "memory");
                 tmem_ld_wait();
-                if (key_ok) {
+                if constexpr (kD == 64) {
+                    // Through shared memory and one TMA store per warpgroup: the warpgroup's own dS^T box of the tile parity that
+                    // the NEXT tile will use (8 KB = 128 keys x 32 columns; free: its dQ MMAs and its TMA reduce are long done).
+                    // The same thread waits for the store to have read the box before the warpgroup writes dS^T there again
+                    // (first tile of the next item).  Rows beyond N are clipped by the tensor map.
+                    uint8_t* stage = smem + C::kDS + ((((kb + n_iter) & 1) * kNSub) + wg) * kBoxBytes;
+#pragma unroll
+                    for (int c0 = 0; c0 < kColsPer; c0 += 8) {
+                        const uint32_t* a = acc + c0;
+                        uint4 out;
+                        out.x = pack2<kBf16>(__uint_as_float(a[0]) * sc, __uint_as_float(a[1]) * sc);
+                        out.y = pack2<kBf16>(__uint_as_float(a[2]) * sc, __uint_as_float(a[3]) * sc);
+                        out.z = pack2<kBf16>(__uint_as_float(a[4]) * sc, __uint_as_float(a[5]) * sc);
+                        out.w = pack2<kBf16>(__uint_as_float(a[6]) * sc, __uint_as_float(a[7]) * sc);
+                        *reinterpret_cast<uint4*>(stage + r * 64 + (((c0 / 8) ^ rx) << 4)) = out;
+                    }
+                    fence_proxy_async_smem();
+                    named_bar_sync(8 + wg, 128);
+                    if (r == 0) {
+                        tma_store_4d(is_dv ? &p.map_dv_st : &p.map_dk_st, stage, c_first, col0, h, b);
+                        bulk_commit_group();
+                    }
+                    store_pending = true;
+                } else if (key_ok) {
 #pragma unroll
                     for (int c0 = 0; c0 < kColsPer; c0 += 8) {
                         const uint32_t* a = acc + c0;
@@ -860,6 +899,7 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
 #ifdef B200T5_BWD_TIMING
         if (threadIdx.x == 0 && blockIdx.x < 8 && it < 20) g_bwd3_item_ts[blockIdx.x][it] = clock64();
 #endif
+        if (store_pending && r == 0) bulk_wait_group_read<0>();   // shared memory must outlive the last dK / dV store
     }
 #undef B200T5_ITEM_BEGIN
 #undef B200T5_ITEM_END

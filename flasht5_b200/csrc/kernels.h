@@ -56,6 +56,7 @@ struct AttnBwdKernelParams {
     const void* v;
     int64_t v_sb, v_sh, v_sn;
     CUtensorMap map_dq;     // 16-bit dQ group surface (D, M, H, dq_groups * B), box (min(D,64), 128, 1, 1), reduce-add
+    CUtensorMap map_dk_st, map_dv_st;   // v3 kernel, D = 64: dK / dV (D, N, H, B) with box (D / 2, 128): one warpgroup's half of a tile (TMA store)
     const void* bias;       // [bias mode 2]
     int64_t bias_sb, bias_sh, bias_sm, bias_sn;
     void* dk;
