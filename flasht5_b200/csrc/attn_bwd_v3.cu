@@ -82,7 +82,7 @@ struct Bwd3Cfg {
     // two whole tiles left the first sub-tile of every other tile waiting ~2 400 cycles for its TMA; a ring of eleven 32-row
     // slots made the single producer lane the pacemaker of the whole CTA: 4 operations + a probe = ~650 cycles per sub-tile,
     // 2 600 per tile against 1 500 of math -- profiles/r2c_bwd_v3_timeline_*.)
-    static constexpr int kSlots = kBiasMode == 0 ? 6 : 4;
+    static constexpr int kSlots = kBiasMode == 0 ? 6 : 5;
     static constexpr int kSlotRows = 2 * kSub;
     static constexpr int kSlotBytes = 2 * kSubTileBytes;
     static constexpr int kK = 0;
@@ -90,8 +90,8 @@ struct Bwd3Cfg {
     static constexpr int kDO = kQ + kSlots * kSlotBytes;
     static constexpr int kDS = kDO + kSlots * kSlotBytes;              // [2 tiles][4 boxes] dS^T
     static constexpr int kDQ = kDS + 2 * kNSub * kBoxBytes;            // dQ staging tile [128][D] io dtype (prologue: the V tile)
-    static constexpr int kBand = kDQ + kTileBytes;                     // relative-position band (mode 3) / bias staging (mode 1), 32 KB
-    static constexpr int kStats = kBand + (kBiasMode == 0 ? 0 : 32768);                     // [kSlots][2][64] fp32: -L*log2e, -delta of the slot's queries
+    static constexpr int kBand = kDQ + kTileBytes;                     // relative-position band (mode 3) / bias staging (mode 1), 16 KB
+    static constexpr int kStats = kBand + (kBiasMode == 0 ? 0 : 16384);                     // [kSlots][2][64] fp32: -L*log2e, -delta of the slot's queries
     static constexpr int kBars = kStats + kSlots * 2 * kSlotRows * 4;
     static constexpr int kNumBars = 2 + 2 * kSlots + 5 * kNSub + 3 + 2 + 2 + 1 + 2;
     static constexpr int kTmemSlot = kBars + kNumBars * 8;
@@ -626,7 +626,10 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
         const bool rpe_skip = kBiasMode == 3 && p.rpe.dconst != nullptr;
         // The 64 bytes of bias this thread needs for its next sub-tile are copied global -> shared with cp.async (no registers:
         // they would be live across a whole sub-tile) into the band's shared memory (mode 3 is the other user): [wg][chunk][row].
-        uint4* const bias_stage = reinterpret_cast<uint4*>(smem + C::kBand) + wg * (4 * 128) + r;
+        // Half a sub-tile (16 queries = 32 bytes per thread) at a time, [wg][2 chunks][128 rows]: the copy of a half is issued right
+        // after the half before it has been read, i.e. ~900 cycles of arithmetic ahead of its use (a whole sub-tile ahead would
+        // need 32 KB, which is the fifth ring slot).
+        uint4* const bias_stage = reinterpret_cast<uint4*>(smem + C::kBand) + wg * (2 * 128) + r;
 
         // K and V rows of a key block, shared memory (TMA, swizzled rows) -> TMEM (the A operands of S^T and dP^T); warpgroup 0.
         // `item_no` = the (non-empty) item they belong to: K sits in buffer item_no & 1 (k_full phase item_no), V in the ring
@@ -685,12 +688,12 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
             const int64_t n_mb = kNSub * p.num_m_blocks;              // the copy covers whole 128-query tiles
             bias_blk = reinterpret_cast<const uint4*>(p.bias) + ((bh * nnb + nb) * n_mb) * (4 * 128) + r;
         }
-        auto load_bias = [&](int kk) {                          // kk: tile (iteration) whose bias is fetched
-            const uint4* src = bias_blk + (int64_t)(((i_start + kk) * kBM + wg * kSub) / kSub) * (4 * 128);
+        auto load_bias = [&](int kk, int half) {                // kk: tile (iteration), half: 16-query half of the sub-tile
+            const uint4* src = bias_blk + (int64_t)(((i_start + kk) * kBM + wg * kSub) / kSub) * (4 * 128) + half * (2 * 128);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) cp_async_16(bias_stage + c * 128, src + c * 128);
+            for (int c = 0; c < 2; ++c) cp_async_16(bias_stage + c * 128, src + c * 128);
         };
-        if (n_iter > 0 && kBiasMode == 1) load_bias(0);
+        if (n_iter > 0 && kBiasMode == 1) load_bias(0, 0);
         if (wg == 0 && n_iter > 0) {
             // dV, dK accumulators start at zero: every dV / dK MMA accumulates (two warps issue them).  Ordered before the first
             // of those MMAs by this warpgroup's first pds_full arrival (tcgen05.wait::st + fence come first) and the B0 -> B1 token.
@@ -739,14 +742,17 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(s_empty + wg);
-            if (kBiasMode == 1) cp_async_wait_all();               // this thread's own copies: nobody else reads them
 #pragma unroll
             for (int hc = 0; hc < 2; ++hc) {
                 uint32_t pp[8], dd[8], bias_h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                 if (kBiasMode == 1) {
-                    const uint4 u0 = bias_stage[(2 * hc) * 128], u1 = bias_stage[(2 * hc + 1) * 128];
+                    cp_async_wait_all();                           // this thread's own copies: nobody else reads them
+                    const uint4 u0 = bias_stage[0], u1 = bias_stage[128];
                     bias_h[0] = u0.x; bias_h[1] = u0.y; bias_h[2] = u0.z; bias_h[3] = u0.w;
                     bias_h[4] = u1.x; bias_h[5] = u1.y; bias_h[6] = u1.z; bias_h[7] = u1.w;
+                    // the next half's copy goes into the same 32 bytes (the two LDS above precede it in the LSU)
+                    if (hc == 0) load_bias(k, 1);
+                    else if (k + 1 < n_iter) load_bias(k + 1, 0);
                 }
                 const uint32_t(&dr)[16] = *reinterpret_cast<const uint32_t(*)[16]>(drr + hc * 16);
                 // statistics of the slot: the S^T MMAs of this sub-tile were issued after warp A saw the slot's barrier complete
@@ -796,7 +802,6 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
             fence_proxy_async_smem();
             mbar_arrive(pds_full + (kg & 1) * kNSub + wg);
             if (r == 0) BWD3_TS(wg, k, 3);
-            if (kBiasMode == 1 && k + 1 < n_iter) load_bias(k + 1);       // lands during the wait for the next S^T
         }
         if (r == 0) BWD3_TS(wg, 8, 0);                        // (row 8 of the timeline: the item boundary)
         if (wg == 0 && n_iter > 0 && next_item(item).n_iter > 0) {

@@ -22,7 +22,7 @@ struct RpeBand {
     float* dconst;          // NULL: every tile stores dS
 };
 constexpr int kRpeBandPad = 255;        // 2 * 128 - 1 relative positions per tile
-constexpr int kRpeMaxBandLen = 8192;    // 32 KB of shared memory (the dense bias ring's space)
+constexpr int kRpeMaxBandLen = 4096;    // 16 KB of shared memory (what the backward kernel can spare beside its K double buffer and a 5-slot ring)
 
 struct AttnFwdKernelParams {
     CUtensorMap map_q;      // (D, M, H, B)   box (min(D,64), 128, 1, 1)

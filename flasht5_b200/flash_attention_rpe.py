@@ -44,7 +44,7 @@ __all__ = ["flash_attention_v2_rpe", "FlashAttentionRPE", "rpe_band", "attn_rpe_
            "bucket_lut", "constant_ends", "band_len", "fused_default", "BAND_PAD", "MAX_BAND_LEN"]
 
 BAND_PAD = 255          # kernels.h: kRpeBandPad
-MAX_BAND_LEN = 8192     # kernels.h: kRpeMaxBandLen
+MAX_BAND_LEN = 4096     # kernels.h: kRpeMaxBandLen
 
 _LUT_CACHE = {}          # (M, N, num_buckets, max_distance, bidirectional, device) -> (lut, lut_zero, const_lo, const_hi)
 _LUT_CACHE_MAX = 64      # shapes a process meets are few; bound it anyway (oldest entry goes first)
