@@ -277,6 +277,10 @@ static int attn_fwd_impl(const b200t5_attn_params* p, const b200t5_rpe_params* r
     if ((rc = make_map_4d(&kp.map_q, p->q, 2, dt, p->D, p->M, p->H, p->B, p->q_strides[2], p->q_strides[1], p->q_strides[0], boxd, 128, "q"))) return rc;
     if ((rc = make_map_4d(&kp.map_k, p->k, 2, dt, p->D, p->N, p->H, p->B, p->k_strides[2], p->k_strides[1], p->k_strides[0], boxd, 128, "k"))) return rc;
     if ((rc = make_map_4d(&kp.map_v, p->v, 2, dt, p->D, p->N, p->H, p->B, p->v_strides[2], p->v_strides[1], p->v_strides[0], boxd, 128, "v"))) return rc;
+    if (p->D == 64) {
+        if (!strides_tma_ok(p->o, p->o_strides, p->B, p->H)) return fail(B200T5_ERR_INVALID, "o needs unit last stride, 16-byte aligned base and other strides that are multiples of 8 elements");
+        if ((rc = make_map_4d(&kp.map_o, p->o, 2, dt, p->D, p->M, p->H, p->B, p->o_strides[2], p->o_strides[1], p->o_strides[0], boxd, 128, "o"))) return rc;
+    }
     int mode = rpe ? 3 : bias_mode_of(p);
     if (mode == 2 && p->workspace && p->workspace_bytes >= fwd_workspace_bytes(p) && reinterpret_cast<uintptr_t>(p->workspace) % 256 == 0) {
         // rows a tensor map cannot address: aligned copy in the caller's workspace, then the TMA path

@@ -538,7 +538,20 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdKernelParams p) {
                 if constexpr (kChunk == 32) tmem_ld32(tm_o + c0, o);
                 else tmem_ld16(tm_o + c0, reinterpret_cast<uint32_t(&)[16]>(o[0]));
                 tmem_ld_wait();
-                if (row_ok) {
+                if constexpr (kD == 64) {
+                    // D = 64: the tile leaves through shared memory (Q's tile: every S MMA is long done) and ONE TMA store.  A
+                    // thread = row store to global memory costs an L1 request per 16 bytes: 1 024 requests per CTA.  Rows beyond
+                    // M are clipped by the tensor map.
+#pragma unroll
+                    for (int i = 0; i < kChunk; i += 8) {
+                        uint4 out;
+                        out.x = pack2<kBf16>(__uint_as_float(o[i + 0]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
+                        out.y = pack2<kBf16>(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+                        out.z = pack2<kBf16>(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
+                        out.w = pack2<kBf16>(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
+                        *reinterpret_cast<uint4*>(smem + L::kQ + r * 128 + ((((c0 + i) / 8) ^ (r & 7)) << 4)) = out;
+                    }
+                } else if (row_ok) {
 #pragma unroll
                     for (int i = 0; i < kChunk; i += 8) {
                         uint4 out;
@@ -551,6 +564,15 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdKernelParams p) {
                 }
             }
             tc_fence_before();
+            if constexpr (kD == 64) {
+                fence_proxy_async_smem();
+                named_bar_sync(1, 128);
+                if (r == 0) {
+                    tma_store_4d(&p.map_o, smem + L::kQ, 0, row0, h, b);
+                    bulk_commit_group();
+                    bulk_wait_group_read<0>();                     // shared memory must outlive the read; the write completes by itself
+                }
+            }
         } else if (row_ok) {
             // every key is masked for this whole block (causal, M > N): O = 0, L = -inf
 #pragma unroll

@@ -29,6 +29,7 @@ struct AttnFwdKernelParams {
     CUtensorMap map_k;      // (D, N, H, B)
     CUtensorMap map_v;      // (D, N, H, B)
     CUtensorMap map_bias;   // (N, M, Hb, Bb) box (64, 128, 1, 1)            [bias mode 1]
+    CUtensorMap map_o;      // (D, M, H, B) box (64, 128, 1, 1): the output tile (TMA store; D = 64)
     const void* bias;       // raw pointer                                   [bias mode 2]
     int64_t bias_sb, bias_sh, bias_sm, bias_sn;   // element strides          [bias mode 2]
     void* o;
