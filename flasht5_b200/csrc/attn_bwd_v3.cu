@@ -398,6 +398,11 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
                     //  completed TWO further phases, which a parity probe cannot tell from none -- found as a deadlock in the
                     //  causal full-shape test)
                     if (it > 0) mbar_wait(kbuf_free + ((it + 1) & 1), ((it - 1) >> 1) & 1);
+                    // k_full takes ONE arrival per phase: K of this item (requested an item ago) must have landed before the
+                    // next phase is armed.  With a one-tile item this lane gets here within a few hundred cycles of that
+                    // request; the second arrival on the open phase was a hardware fault (mbarrier arrival-count underflow),
+                    // seen as sporadic "unspecified launch failure" on the causal no-bias shapes.
+                    mbar_wait(k_full, it & 1);
                     mbar_arrive_expect_tx(k_full, C::kTileBytes);
                     tma_load_4d(smem + C::kK + ((it + 1) & 1) * C::kTileBytes, &p.map_k, k_full, 0, wn.col0, wn.h, wn.b);
                 }
