@@ -129,7 +129,7 @@ def _fwd_kernel_bias(band_row, band_lo, lo, hi, M, N):
 
 
 def _bwd_kernel_bias(band_row, band_lo, lo, hi, M, N):
-    """Index arithmetic of attn_bwd_v2.cu / attn_bwd.cu (bias mode 3): CTA = 128-key block, loop over query blocks,
+    """Index arithmetic of attn_bwd_v3.cu / attn_bwd.cu (bias mode 3): CTA = 128-key block, loop over query blocks,
     warpgroup wg owns 64 columns, chunks of 32 (v2) -- the 8-column groups of attn_bwd.cu index the same addresses."""
     Mp, Np = -(-M // 128) * 128, -(-N // 128) * 128
     out = torch.empty(Mp, Np, dtype=band_row.dtype)
