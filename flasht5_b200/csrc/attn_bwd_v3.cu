@@ -403,6 +403,10 @@ attn_bwd_kernel_v3(const __grid_constant__ AttnBwdKernelParams p) {
                     // request; the second arrival on the open phase was a hardware fault (mbarrier arrival-count underflow),
                     // seen as sporadic "unspecified launch failure" on the causal no-bias shapes.
                     mbar_wait(k_full, it & 1);
+                    // ... and every warp of warpgroup 0 must have SEEN that phase (they arrive on kt_ready after their copy): a
+                    // warp that loses the scheduler before its k_full probe would otherwise find the barrier two phases on
+                    // and wait for ever (found by the protocol model, tests/test_bwd_protocol_model.py; long complete here)
+                    mbar_wait(kt_ready, it & 1);
                     mbar_arrive_expect_tx(k_full, C::kTileBytes);
                     tma_load_4d(smem + C::kK + ((it + 1) & 1) * C::kTileBytes, &p.map_k, k_full, 0, wn.col0, wn.h, wn.b);
                 }
