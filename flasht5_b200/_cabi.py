@@ -98,7 +98,7 @@ SYMBOLS = {
     "b200t5_profile_enable": (_i32, [_i32]),
     "b200t5_profile_collect": (_i32, [C.POINTER(C.c_int), C.POINTER(C.c_float), _i32]),
 }
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _lib = None
 _lock = threading.Lock()

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B200T5_ABI_VERSION 2
+#define B200T5_ABI_VERSION 3   /* 3: attn flags (was reserved0), b200t5_attn_fwd_workspace_bytes */
 
 #if defined(__GNUC__)
 #define B200T5_API __attribute__((visibility("default")))
